@@ -28,6 +28,9 @@
 extern "C" {
 #endif
 
+/* exported from libtrlda_b200.so (everything else in the library has hidden visibility) */
+#define TRLDA_API __attribute__((visibility("default")))
+
 #define TRLDA_OK            0
 #define TRLDA_ERR_ARG       1   /* reference would have thrown TRLDA::Exception -> RuntimeError */
 #define TRLDA_ERR_CUDA      2   /* CUDA / NCCL failure, or no device                              */
@@ -73,7 +76,7 @@ typedef struct trlda_params {
 } trlda_params;
 
 /* fills in the defaults of LDA::Parameters::Parameters (lda.h:56-77) */
-void trlda_params_default(trlda_params* p);
+TRLDA_API void trlda_params_default(trlda_params* p);
 
 /* CSR view of `LDA::Documents` (host memory, not owned) */
 typedef struct trlda_docs {
@@ -94,7 +97,7 @@ typedef struct trlda_stats {
 	int64_t h2d_bytes;                          /* host->device bytes since the last reset                  */
 	int64_t d2h_bytes;                          /* device->host bytes since the last reset                  */
 } trlda_stats;
-const char* trlda_kernel_kind_name(int kind);
+TRLDA_API const char* trlda_kernel_kind_name(int kind);
 
 /* ---- lifetime -------------------------------------------------------------------------------------------- */
 
@@ -102,30 +105,30 @@ const char* trlda_kernel_kind_name(int kind);
  * (onlinelda.cpp:18-49, batchlda.cpp:22-39, cumulativelda.cpp:22-45).  `alpha` points to K values.
  * lambda is initialised ~ Gamma(100, 1/100) (lda.cpp:71) by the device generator (Cumulative: lambda = eta,
  * cumulativelda.cpp:30).  `num_documents` is ignored for Batch/Cumulative.  `device` is a CUDA ordinal. */
-int trlda_create(int kind, int num_words, int num_topics, int64_t num_documents,
+TRLDA_API int trlda_create(int kind, int num_words, int num_topics, int64_t num_documents,
                  const double* alpha, double eta, int device, int precision, trlda_model** out);
-void trlda_destroy(trlda_model* m);   /* Distribution_dealloc, python/src/distributioninterface.cpp:30-37 */
-const char* trlda_last_error(const trlda_model* m);
+TRLDA_API void trlda_destroy(trlda_model* m);   /* Distribution_dealloc, python/src/distributioninterface.cpp:30-37 */
+TRLDA_API const char* trlda_last_error(const trlda_model* m);
 
 /* process-wide generator seed; replaces `trlda.seed` -> srand (python/src/module.cpp:332-342) */
-void trlda_seed(uint64_t seed);
+TRLDA_API void trlda_seed(uint64_t seed);
 
 /* ---- accessors (lda.h:140-201, onlinelda.h:50-74) ---------------------------------------------------------- */
-int trlda_kind(const trlda_model* m);
-int trlda_precision(const trlda_model* m);
-int trlda_set_precision(trlda_model* m, int precision);
-int trlda_num_topics(const trlda_model* m);                        /* LDA::numTopics  lda.h:194 */
-int trlda_num_words(const trlda_model* m);                         /* LDA::numWords   lda.h:200 */
-int trlda_get_lambda(trlda_model* m, double* lambda_KxV);          /* LDA::lambda     lda.h:180 */
-int trlda_set_lambda(trlda_model* m, const double* lambda_KxV, int rows, int cols);  /* LDA::setLambda lda.h:186 */
-int trlda_get_alpha(trlda_model* m, double* alpha_K);              /* LDA::alpha      lda.h:140 */
-int trlda_set_alpha(trlda_model* m, const double* alpha, int n);   /* LDA::setAlpha   lda.h:146-160 (n==1: scalar form) */
-int trlda_get_eta(trlda_model* m, double* eta);                    /* LDA::eta        lda.h:164 */
-int trlda_set_eta(trlda_model* m, double eta);                     /* LDA::setEta     lda.h:170 */
-int trlda_get_num_documents(trlda_model* m, int64_t* n);           /* OnlineLDA::numDocuments    onlinelda.h:50 */
-int trlda_set_num_documents(trlda_model* m, int64_t n);            /* OnlineLDA::setNumDocuments onlinelda.h:56 */
-int trlda_get_update_count(trlda_model* m, int64_t* n);            /* OnlineLDA::updateCount     onlinelda.h:64 */
-int trlda_set_update_count(trlda_model* m, int64_t n);             /* OnlineLDA::setUpdateCount  onlinelda.h:70 */
+TRLDA_API int trlda_kind(const trlda_model* m);
+TRLDA_API int trlda_precision(const trlda_model* m);
+TRLDA_API int trlda_set_precision(trlda_model* m, int precision);
+TRLDA_API int trlda_num_topics(const trlda_model* m);                        /* LDA::numTopics  lda.h:194 */
+TRLDA_API int trlda_num_words(const trlda_model* m);                         /* LDA::numWords   lda.h:200 */
+TRLDA_API int trlda_get_lambda(trlda_model* m, double* lambda_KxV);          /* LDA::lambda     lda.h:180 */
+TRLDA_API int trlda_set_lambda(trlda_model* m, const double* lambda_KxV, int rows, int cols);  /* LDA::setLambda lda.h:186 */
+TRLDA_API int trlda_get_alpha(trlda_model* m, double* alpha_K);              /* LDA::alpha      lda.h:140 */
+TRLDA_API int trlda_set_alpha(trlda_model* m, const double* alpha, int n);   /* LDA::setAlpha   lda.h:146-160 (n==1: scalar form) */
+TRLDA_API int trlda_get_eta(trlda_model* m, double* eta);                    /* LDA::eta        lda.h:164 */
+TRLDA_API int trlda_set_eta(trlda_model* m, double eta);                     /* LDA::setEta     lda.h:170 */
+TRLDA_API int trlda_get_num_documents(trlda_model* m, int64_t* n);           /* OnlineLDA::numDocuments    onlinelda.h:50 */
+TRLDA_API int trlda_set_num_documents(trlda_model* m, int64_t n);            /* OnlineLDA::setNumDocuments onlinelda.h:56 */
+TRLDA_API int trlda_get_update_count(trlda_model* m, int64_t* n);            /* OnlineLDA::updateCount     onlinelda.h:64 */
+TRLDA_API int trlda_set_update_count(trlda_model* m, int64_t n);             /* OnlineLDA::setUpdateCount  onlinelda.h:70 */
 
 /* ---- the hot path -------------------------------------------------------------------------------------------- */
 
@@ -133,24 +136,24 @@ int trlda_set_update_count(trlda_model* m, int64_t n);             /* OnlineLDA:
  * `latents` = initial gamma, K x B column-major, or NULL to draw gamma0 ~ Gamma(100, 1/100) on the device
  * (lda.cpp:135).  latents_rows/latents_cols are validated like lda.cpp:165 ("Initial gamma has wrong
  * dimensionality.").  gamma_out (K x B) and sstats_out (K x V) may each be NULL to skip the copy-out. */
-int trlda_update_variables(trlda_model* m, const trlda_docs* docs,
+TRLDA_API int trlda_update_variables(trlda_model* m, const trlda_docs* docs,
                            const double* latents, int latents_rows, int64_t latents_cols,
                            const trlda_params* params, double* gamma_out, double* sstats_out);
 
 /* LDA::updateParameters: OnlineLDA (onlinelda.cpp:53-180), BatchLDA (batchlda.cpp:43-209),
  * CumulativeLDA (cumulativelda.cpp:49-153).  `*result` receives the reference's return value (the learning
  * rate rho for Online; 1.0 for Batch/Cumulative and for an empty batch). */
-int trlda_update_parameters(trlda_model* m, const trlda_docs* docs, const trlda_params* params, double* result);
+TRLDA_API int trlda_update_parameters(trlda_model* m, const trlda_docs* docs, const trlda_params* params, double* result);
 
 /* Same as trlda_update_parameters but on the minibatch already resident in HBM (trlda_upload_docs): the
  * device-only leg of bench.py.  No host<->device traffic except the returned scalar. */
-int trlda_upload_docs(trlda_model* m, const trlda_docs* docs);
-int trlda_update_parameters_resident(trlda_model* m, const trlda_params* params, double* result);
+TRLDA_API int trlda_upload_docs(trlda_model* m, const trlda_docs* docs);
+TRLDA_API int trlda_update_parameters_resident(trlda_model* m, const trlda_params* params, double* result);
 
 /* LDA::lowerBound (lda.cpp:297-360; OnlineLDA::lowerBound onlinelda.cpp:184-191).  Follows the INTENDED
  * bound (tests/onlineldavb.py:260-318); lda.cpp:334 mis-indexes a K x V array and is not reproduced.
  * per_doc_out (B values, may be NULL) receives the per-document terms before the num_documents factor. */
-int trlda_lower_bound(trlda_model* m, const trlda_docs* docs, const double* latents, int latents_rows,
+TRLDA_API int trlda_lower_bound(trlda_model* m, const trlda_docs* docs, const double* latents, int latents_rows,
                       int64_t latents_cols, const trlda_params* params, int64_t num_documents,
                       double* bound_out, double* per_doc_out);
 
@@ -159,33 +162,33 @@ int trlda_lower_bound(trlda_model* m, const trlda_docs* docs, const double* late
  * inside updateParameters and offers no way to pass them in.  These two calls install values that the NEXT
  * trlda_update_parameters / trlda_lower_bound call uses wherever the reference would have drawn fresh ones
  * (every fresh-gamma E-step of that call uses the same gamma0).  They are consumed by that call. */
-int trlda_inject_initial_gamma(trlda_model* m, const double* gamma0_KxB, int rows, int64_t cols);
-int trlda_inject_initial_lambda(trlda_model* m, const double* lambda_KxV, int rows, int cols);
+TRLDA_API int trlda_inject_initial_gamma(trlda_model* m, const double* gamma0_KxB, int rows, int64_t cols);
+TRLDA_API int trlda_inject_initial_lambda(trlda_model* m, const double* lambda_KxV, int rows, int cols);
 
 /* ---- multi-GPU: documents sharded over ranks, one exchange of the sufficient statistics per E-step ----------
  * One process per GPU.  Rank 0 obtains an id, the host plumbing broadcasts its 128 bytes, every rank calls
  * trlda_comm_init.  Afterwards `docs` passed to the hot-path calls are THIS RANK'S shard; batch-wide
  * quantities (B, word counts, sstats, alpha statistics) are summed over ranks with NCCL on the model's
  * stream.  All ranks must hold identical lambda/alpha/eta and make the same calls. */
-int trlda_comm_unique_id(void* id_out_128_bytes);
-int trlda_comm_init(trlda_model* m, const void* id_128_bytes, int rank, int nranks);
-int trlda_comm_size(const trlda_model* m);
+TRLDA_API int trlda_comm_unique_id(void* id_out_128_bytes);
+TRLDA_API int trlda_comm_init(trlda_model* m, const void* id_128_bytes, int rank, int nranks);
+TRLDA_API int trlda_comm_size(const trlda_model* m);
 
 /* ---- instrumentation ------------------------------------------------------------------------------------------ */
-void* trlda_stream(trlda_model* m);                 /* the cudaStream_t all kernels of this model run on */
-int trlda_synchronize(trlda_model* m);
-int trlda_set_profiling(trlda_model* m, int on);    /* bracket every kernel with CUDA events              */
-int trlda_get_stats(trlda_model* m, trlda_stats* out);
-int trlda_reset_stats(trlda_model* m);
-int trlda_get_row_sums(trlda_model* m, double* row_sums_K);   /* sum_w lambda_kw, a cheap per-step result */
+TRLDA_API void* trlda_stream(trlda_model* m);                 /* the cudaStream_t all kernels of this model run on */
+TRLDA_API int trlda_synchronize(trlda_model* m);
+TRLDA_API int trlda_set_profiling(trlda_model* m, int on);    /* bracket every kernel with CUDA events              */
+TRLDA_API int trlda_get_stats(trlda_model* m, trlda_stats* out);
+TRLDA_API int trlda_reset_stats(trlda_model* m);
+TRLDA_API int trlda_get_row_sums(trlda_model* m, double* row_sums_K);   /* sum_w lambda_kw, a cheap per-step result */
 
 /* device special functions evaluated on n host values (test hook pinning the in-kernel psi / psi' / lgamma
  * against python/tests/utils_test.py:33-51): which = 0 digamma fp64, 1 trigamma fp64, 2 lgamma fp64,
  * 3 exp(digamma) as evaluated by the mixed-precision E-step. */
-int trlda_device_special(int device, int which, const double* x, int64_t n, double* out);
+TRLDA_API int trlda_device_special(int device, int which, const double* x, int64_t n, double* out);
 
 /* host special functions used by the Newton steps: polygamma(n, x) of utils.cpp:107-111 (n = 0, 1, 2) */
-double trlda_polygamma(int n, double x);
+TRLDA_API double trlda_polygamma(int n, double x);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,960 @@
+// kernels.cu — hand-written sm_100a kernels of the trlda hot path.
+//
+// Data layout in HBM (all column-major, the reference's Eigen layout, so a word's K-vector is contiguous):
+//   lambda, lambda', sstats   K x V float64
+//   beta = expElogbeta        K x V float64 (fp64 mode) or float32 (mixed mode)
+//   gamma, etheta, doc_stat   K x B float64 (+ a float32 copy of etheta in mixed mode)
+//   minibatch                 CSR (doc_ptr, word_ids, counts) + word-sorted token list (word_ptr, tok_doc, tok_src)
+//
+// Reference citations are relative to /root/reference/code/trlda/src/.
+#include "kernels.cuh"
+#include "special.cuh"
+
+#include <cooperative_groups.h>
+#include <math_constants.h>
+#include <algorithm>
+#include <cstdio>
+
+namespace cg = cooperative_groups;
+
+namespace trlda {
+
+static inline int ceil_div(int64_t a, int64_t b) { return (int) ((a + b - 1) / b); }
+static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+// ------------------------------------------------------------------------------------------------------------
+// block-level helpers
+// ------------------------------------------------------------------------------------------------------------
+
+// deterministic block sum; every thread gets the result.  `scratch` holds >= 32 doubles.
+__device__ __forceinline__ double block_sum(double v, double* scratch) {
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+	v = warp_sum(v);
+	__syncthreads();
+	if(lane == 0)
+		scratch[warp] = v;
+	__syncthreads();
+	double total = 0.0;
+	for(int i = 0; i < nw; ++i)
+		total += scratch[i];
+	return total;
+}
+
+template <typename T> __device__ __forceinline__ T load_as(const void* p, int64_t i);
+template <> __device__ __forceinline__ double load_as<double>(const void* p, int64_t i) { return static_cast<const double*>(p)[i]; }
+template <> __device__ __forceinline__ float load_as<float>(const void* p, int64_t i) { return static_cast<const float*>(p)[i]; }
+
+// ------------------------------------------------------------------------------------------------------------
+// row sums of a K x V column-major matrix (lda.cpp:172 `mLambda.rowwise().sum()`), two deterministic stages
+// ------------------------------------------------------------------------------------------------------------
+constexpr int ROWSUM_CHUNK = 128;
+
+__global__ void __launch_bounds__(256) k_rowsum_partial(const double* __restrict__ m, int K, int V, double* __restrict__ partials) {
+	const int k = blockIdx.y * 256 + threadIdx.x;
+	if(k >= K)
+		return;
+	const int w0 = blockIdx.x * ROWSUM_CHUNK, w1 = min(V, w0 + ROWSUM_CHUNK);
+	double acc = 0.0;
+	#pragma unroll 4
+	for(int w = w0; w < w1; ++w)
+		acc += m[(int64_t) w * K + k];
+	partials[(int64_t) blockIdx.x * K + k] = acc;
+}
+
+__global__ void __launch_bounds__(256) k_reduce_partials(const double* __restrict__ partials, int P, int K, double* __restrict__ out) {
+	const int k = blockIdx.x * 256 + threadIdx.x;
+	if(k >= K)
+		return;
+	double acc = 0.0;
+	for(int p = 0; p < P; ++p)
+		acc += partials[(int64_t) p * K + k];
+	out[k] = acc;
+}
+
+int rowsum_num_partials(int V) { return ceil_div(V, ROWSUM_CHUNK); }
+
+void launch_rowsum(const double* lambda, int K, int V, double* partials, int* num_partials, cudaStream_t s) {
+	const int P = rowsum_num_partials(V);
+	k_rowsum_partial<<<dim3(P, ceil_div(K, 256)), 256, 0, s>>>(lambda, K, V, partials);
+	if(num_partials)
+		*num_partials = P;
+}
+
+void launch_reduce_partials(const double* partials, int P, int K, double* out, cudaStream_t s) {
+	k_reduce_partials<<<ceil_div(K, 256), 256, 0, s>>>(partials, P, K, out);
+}
+
+__global__ void k_psi_vector(const double* __restrict__ in, int K, double* __restrict__ out) {
+	const int k = blockIdx.x * blockDim.x + threadIdx.x;
+	if(k < K)
+		out[k] = digamma(in[k]);
+}
+
+void launch_psi_vector(const double* in, int K, double* out, cudaStream_t s) {
+	k_psi_vector<<<ceil_div(K, 128), 128, 0, s>>>(in, K, out);
+}
+
+__global__ void k_lgamma_vector(const double* __restrict__ in, int K, double* __restrict__ out) {
+	const int k = blockIdx.x * blockDim.x + threadIdx.x;
+	if(k < K)
+		out[k] = lgamma(in[k]);
+}
+
+void launch_lgamma_vector(const double* in, int K, double* out, cudaStream_t s) {
+	k_lgamma_vector<<<ceil_div(K, 128), 128, 0, s>>>(in, K, out);
+}
+
+__global__ void k_rows_update(const double* __restrict__ prev, const double* __restrict__ stat, double a, double b, double c,
+                              int K, double* __restrict__ rows_new, double* __restrict__ psi_rows) {
+	const int k = blockIdx.x * blockDim.x + threadIdx.x;
+	if(k >= K)
+		return;
+	const double r = a * (prev ? prev[k] : 0.0) + b + c * (stat ? stat[k] : 0.0);
+	rows_new[k] = r;
+	psi_rows[k] = digamma(r);
+}
+
+void launch_rows_update(const double* rows_prev, const double* rows_stat, double a, double b, double c, int K,
+                        double* rows_new, double* psi_rows, cudaStream_t s) {
+	k_rows_update<<<ceil_div(K, 128), 128, 0, s>>>(rows_prev, rows_stat, a, b, c, K, rows_new, psi_rows);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// beta-prep: expElogbeta_kw = exp(psi(lambda_kw) - psi(sum_w lambda_kw))   (lda.cpp:172-173)
+// One word (K contiguous values) per CTA iteration; streaming, read 8 B + write sizeof(T) per element.
+// ------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_beta_prep(const double* __restrict__ lambda, const double* __restrict__ psi_rows,
+                                                   int K, int V, T* __restrict__ beta, double* __restrict__ psi_partials) {
+	__shared__ double scratch[32];
+	for(int w = blockIdx.x; w < V; w += gridDim.x) {
+		double psum = 0.0;
+		for(int k = threadIdx.x; k < K; k += blockDim.x) {
+			const int64_t i = (int64_t) w * K + k;
+			const double p = digamma(lambda[i]);
+			psum += p;
+			beta[i] = (T) exp(p - psi_rows[k]);
+		}
+		if(psi_partials) {
+			const double total = block_sum(psum, scratch);
+			if(threadIdx.x == 0)
+				psi_partials[w] = total;
+		}
+	}
+}
+
+static inline int block_for_k(int K) { return std::min(256, std::max(32, round_up(K, 32))); }
+
+void launch_beta_prep(const double* lambda, const double* psi_rows, int K, int V, void* beta, int elem_size,
+                      double* psi_partials, cudaStream_t s) {
+	const int block = block_for_k(K);
+	const int grid = std::min(V, 148 * 16);
+	if(elem_size == 8)
+		k_beta_prep<double><<<grid, block, 0, s>>>(lambda, psi_rows, K, V, static_cast<double*>(beta), psi_partials);
+	else
+		k_beta_prep<float><<<grid, block, 0, s>>>(lambda, psi_rows, K, V, static_cast<float*>(beta), psi_partials);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// per-document E-step: the gamma/phi fixed point of lda.cpp:174-204
+//
+// One thread-block cluster of C CTAs per document.  The K x n_d tile of expElogbeta columns is split BY TOPIC
+// ROWS across the CTAs (kc rows each) and kept in shared memory for the whole fixed point, so HBM sees each
+// column once.  Splitting by rows makes the gamma update, psi and exp local to a CTA; the only cross-CTA
+// traffic per inner iteration is the n_d partial phi-norms (+1 scalar for the convergence test), exchanged
+// through distributed shared memory: every CTA pushes its partials to the column's owner CTA, the owner sums
+// them in rank order (deterministic) and pushes c_j/phiNorm_j back to all CTAs.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int ESTEP_THREADS = 256;
+
+struct EStepSmem {
+	// byte offsets into dynamic shared memory
+	size_t tile, W, W32, P, dpart, gam, eth, eth32, red, wid, cnt, total;
+};
+
+__host__ __device__ inline EStepSmem estep_smem_layout(int C, int kc, int n_cap, int n_fit, int elem) {
+	EStepSmem L;
+	const int nl_cap = (n_cap + C - 1) / C;
+	size_t o = 0;
+	auto take = [&o](size_t bytes) { size_t at = o; o += (bytes + 15) & ~size_t(15); return at; };
+	L.tile = take((size_t) n_fit * kc * elem);
+	L.W = take((size_t) n_cap * 8);
+	L.W32 = take((size_t) n_cap * 4);
+	L.P = take((size_t) C * nl_cap * 8);
+	L.dpart = take((size_t) C * 8);
+	L.gam = take((size_t) kc * 8);
+	L.eth = take((size_t) kc * 8);
+	L.eth32 = take((size_t) kc * 4);
+	L.red = take((size_t) ESTEP_THREADS * 8);
+	L.wid = take((size_t) n_cap * 4);
+	L.cnt = take((size_t) n_cap * 4);
+	L.total = o;
+	return L;
+}
+
+EStepPlan plan_estep(int K, int n_max, int elem, int smem_optin, int force_cluster) {
+	EStepPlan best;
+	const int n_cap = std::max(32, round_up(n_max, 32));
+	const size_t budget_full = (size_t) smem_optin - 1024;          // 1 KB per CTA is reserved by the driver
+	const size_t budget_half = ((size_t) smem_optin + 1024) / 2 - 2048;   // two CTAs per SM
+	int candidates[4] = {1, 2, 4, 8};
+	int chosen = -1;
+	// pass 0: smallest cluster whose full tile fits twice per SM; pass 1: fits once per SM
+	for(int pass = 0; pass < 2 && chosen < 0; ++pass)
+		for(int ci = 0; ci < 4; ++ci) {
+			const int C = candidates[ci];
+			if(force_cluster > 0 && C != force_cluster)
+				continue;
+			const int kc = round_up(ceil_div(K, C), 32);
+			if((C - 1) * kc >= K && C > 1)
+				continue;                                              // a CTA without rows
+			if(kc > 256 && C < 8 && force_cluster <= 0)
+				continue;
+			const EStepSmem L = estep_smem_layout(C, kc, n_cap, n_cap, elem);
+			if(L.total <= (pass == 0 ? budget_half : budget_full)) {
+				chosen = C;
+				break;
+			}
+		}
+	int C = chosen;
+	if(C < 0) {
+		// nothing fits entirely: largest usable cluster, keep as many columns on chip as fit
+		C = force_cluster > 0 ? force_cluster : 8;
+		while(C > 1 && (C - 1) * round_up(ceil_div(K, C), 32) >= K)
+			C /= 2;
+	}
+	const int kc = round_up(ceil_div(K, C), 32);
+	int n_fit = n_cap;
+	EStepSmem L = estep_smem_layout(C, kc, n_cap, n_fit, elem);
+	if(L.total > budget_full) {
+		const EStepSmem L0 = estep_smem_layout(C, kc, n_cap, 0, elem);
+		n_fit = L0.total >= budget_full ? 0 : (int) ((budget_full - L0.total) / ((size_t) kc * elem));
+		n_fit = n_fit / 4 * 4;
+		L = estep_smem_layout(C, kc, n_cap, n_fit, elem);
+	}
+	best.cluster = C;
+	best.kc = kc;
+	best.n_cap = n_cap;
+	best.n_fit = n_fit;
+	best.smem = L.total;
+	return best;
+}
+
+template <typename T, bool CLUSTERED>
+__global__ void __launch_bounds__(ESTEP_THREADS)
+k_estep(EStepArgs a, DeviceDocs docs, int C, int kc, int n_cap, int n_fit) {
+	extern __shared__ __align__(16) unsigned char smem[];
+	const EStepSmem L = estep_smem_layout(C, kc, n_cap, n_fit, (int) sizeof(T));
+	T* tile = reinterpret_cast<T*>(smem + L.tile);
+	double* W = reinterpret_cast<double*>(smem + L.W);
+	float* W32 = reinterpret_cast<float*>(smem + L.W32);
+	double* P = reinterpret_cast<double*>(smem + L.P);
+	double* dpart = reinterpret_cast<double*>(smem + L.dpart);
+	double* gam = reinterpret_cast<double*>(smem + L.gam);
+	double* eth = reinterpret_cast<double*>(smem + L.eth);
+	float* eth32 = reinterpret_cast<float*>(smem + L.eth32);
+	double* red = reinterpret_cast<double*>(smem + L.red);
+	int* wid = reinterpret_cast<int*>(smem + L.wid);
+	int* cnt = reinterpret_cast<int*>(smem + L.cnt);
+
+	cg::cluster_group cluster = cg::this_cluster();
+	const int rank = CLUSTERED ? (int) cluster.block_rank() : 0;
+	const int64_t d = blockIdx.x / C;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	constexpr int NW = ESTEP_THREADS / 32;
+	const int K = a.K;
+	const int k0 = rank * kc;
+	const int kn = max(0, min(kc, K - k0));                      // rows of this CTA
+	const int64_t begin = docs.doc_ptr[d];
+	const int n = (int) (docs.doc_ptr[d + 1] - begin);
+	const int n_in = min(n, n_fit);                              // columns resident in shared memory
+	const int nl_cap = (n_cap + C - 1) / C;
+	const T* __restrict__ beta = static_cast<const T*>(a.beta);
+	constexpr bool F32 = sizeof(T) == 4;
+
+	// ---- stage the document, the gamma slice and the tile ----------------------------------------------------
+	for(int j = tid; j < n; j += ESTEP_THREADS) {
+		wid[j] = docs.word_ids[begin + j];
+		cnt[j] = docs.counts[begin + j];
+	}
+	for(int r = tid; r < kc; r += ESTEP_THREADS) {
+		double g = 0.0, e = 0.0;
+		if(r < kn) {
+			g = a.gamma[d * K + k0 + r];
+			e = exp_digamma(g);                                   // lda.cpp:174
+		}
+		gam[r] = g;
+		eth[r] = e;
+		eth32[r] = (float) e;
+	}
+	__syncthreads();
+	for(int j = warp; j < n_in; j += NW) {
+		const T* col = beta + (int64_t) wid[j] * K + k0;
+		for(int r = lane; r < kc; r += 32)
+			tile[(size_t) j * kc + r] = r < kn ? col[r] : T(0);
+	}
+	__syncthreads();
+
+	// phiNorm partials of this CTA's rows, pushed to the owner of each column (lda.cpp:183,199)
+	auto pass2_push = [&](double delta_part) {
+		for(int j = warp; j < n; j += NW) {
+			double part;
+			if(F32) {
+				float acc = 0.f;
+				if(j < n_in) {
+					const T* col = tile + (size_t) j * kc;
+					for(int r = lane; r < kc; r += 32)
+						acc = fmaf(eth32[r], (float) col[r], acc);
+				} else {
+					const T* col = beta + (int64_t) wid[j] * K + k0;
+					for(int r = lane; r < kn; r += 32)
+						acc = fmaf(eth32[r], (float) col[r], acc);
+				}
+				part = (double) acc;
+			} else {
+				double acc = 0.0;
+				if(j < n_in) {
+					const T* col = tile + (size_t) j * kc;
+					for(int r = lane; r < kc; r += 32)
+						acc = fma(eth[r], (double) col[r], acc);
+				} else {
+					const T* col = beta + (int64_t) wid[j] * K + k0;
+					for(int r = lane; r < kn; r += 32)
+						acc = fma(eth[r], (double) col[r], acc);
+				}
+				part = acc;
+			}
+			part = warp_sum(part);
+			if(lane == 0) {
+				const int owner = j % C, jl = j / C;
+				double* dst = CLUSTERED ? cluster.map_shared_rank(P, owner) : P;
+				dst[rank * nl_cap + jl] = part;
+			}
+		}
+		if(tid < C) {
+			double* dst = CLUSTERED ? cluster.map_shared_rank(dpart, tid) : dpart;
+			dst[rank] = delta_part;
+		}
+	};
+
+	// owner side: sum the partials in rank order, form c_j / phiNorm_j and broadcast it to every CTA.
+	// Returns the cluster-wide sum of |delta gamma| (identical bits in every CTA).
+	auto exchange = [&]() -> double {
+		if(CLUSTERED) cluster.sync(); else __syncthreads();
+		double delta = 0.0;
+		for(int src = 0; src < C; ++src)
+			delta += dpart[src];
+		for(int jl = tid; jl * C + rank < n; jl += ESTEP_THREADS) {
+			const int j = jl * C + rank;
+			double phi = 0.0;
+			for(int src = 0; src < C; ++src)
+				phi += P[src * nl_cap + jl];
+			phi += 1e-100;
+			const double wv = (double) cnt[j] / phi;
+			for(int dst = 0; dst < C; ++dst) {
+				double* Wd = CLUSTERED ? cluster.map_shared_rank(W, dst) : W;
+				float* Wf = CLUSTERED ? cluster.map_shared_rank(W32, dst) : W32;
+				Wd[j] = wv;
+				Wf[j] = (float) wv;
+			}
+		}
+		if(CLUSTERED) cluster.sync(); else __syncthreads();
+		return delta;
+	};
+
+	// sum_j W_j tile[j][row] for this thread's (row, column-split); the splits are combined through `red`
+	const int R = min(kc, ESTEP_THREADS);
+	const int S = ESTEP_THREADS / R;
+	const int r0 = tid % R, sp = tid / R;
+	auto pass1_partial = [&](int row) -> double {
+		if(F32) {
+			float acc = 0.f;
+			for(int j = sp; j < n_in; j += S)
+				acc = fmaf(W32[j], (float) tile[(size_t) j * kc + row], acc);
+			if(row < kn)
+				for(int j = n_in + sp; j < n; j += S)
+					acc = fmaf(W32[j], (float) beta[(int64_t) wid[j] * K + k0 + row], acc);
+			return (double) acc;
+		} else {
+			double acc = 0.0;
+			for(int j = sp; j < n_in; j += S)
+				acc = fma(W[j], (double) tile[(size_t) j * kc + row], acc);
+			if(row < kn)
+				for(int j = n_in + sp; j < n; j += S)
+					acc = fma(W[j], (double) beta[(int64_t) wid[j] * K + k0 + row], acc);
+			return acc;
+		}
+	};
+
+	pass2_push(0.0);
+	exchange();
+
+	int it = 0;
+	for(; it < a.max_iter; ) {
+		// ---- gamma update (lda.cpp:186-197) ----------------------------------------------------------------------
+		double delta_local = 0.0;
+		for(int rb = 0; rb < kc; rb += R) {
+			const int row = rb + r0;
+			const bool active = sp < S && row < kc;
+			if(active)
+				red[sp * R + r0] = pass1_partial(row);
+			__syncthreads();
+			if(active && sp == 0 && row < kn) {
+				double acc = 0.0;
+				for(int q = 0; q < S; ++q)
+					acc += red[q * R + r0];
+				const double g_old = gam[row];
+				double g_new = acc * eth[row];
+				g_new += a.alpha[k0 + row];
+				delta_local += fabs(g_old - g_new);
+				gam[row] = g_new;
+				const double e = exp_digamma(g_new);
+				eth[row] = e;
+				eth32[row] = (float) e;
+			}
+			__syncthreads();
+		}
+		const double delta_part = block_sum(delta_local, red);
+		__syncthreads();
+		// ---- phiNorm with the new exp(psi(gamma)) (lda.cpp:199), exchange, convergence test (lda.cpp:202) -----------
+		pass2_push(delta_part);
+		const double delta = exchange();
+		++it;
+		if(delta / K < a.threshold)
+			break;
+	}
+
+	// ---- results: gamma, exp(psi(gamma)), token weights, the document's contribution to the row sums of sstats ---
+	for(int r = tid; r < kn; r += ESTEP_THREADS) {
+		a.gamma[d * K + k0 + r] = gam[r];
+		a.etheta[d * K + k0 + r] = eth[r];
+		if(a.etheta32)
+			a.etheta32[d * K + k0 + r] = eth32[r];
+	}
+	for(int j = tid * C + rank; j < n; j += ESTEP_THREADS * C)
+		a.weight[begin + j] = W[j];
+	if(a.doc_stat) {
+		for(int rb = 0; rb < kc; rb += R) {
+			const int row = rb + r0;
+			const bool active = sp < S && row < kc;
+			if(active)
+				red[sp * R + r0] = pass1_partial(row);
+			__syncthreads();
+			if(active && sp == 0 && row < kn) {
+				double acc = 0.0;
+				for(int q = 0; q < S; ++q)
+					acc += red[q * R + r0];
+				a.doc_stat[d * K + k0 + row] = acc * eth[row];
+			}
+			__syncthreads();
+		}
+	}
+	if(rank == 0 && tid == 0 && a.iterations)
+		a.iterations[d] = it;
+}
+
+static int g_estep_smem_optin = 0;
+
+void configure_estep(int smem_optin) {
+	g_estep_smem_optin = smem_optin;
+	cudaFuncSetAttribute(k_estep<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin);
+	cudaFuncSetAttribute(k_estep<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin);
+	cudaFuncSetAttribute(k_estep<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin);
+	cudaFuncSetAttribute(k_estep<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin);
+}
+
+template <typename T, bool CLUSTERED>
+static void launch_estep_t(const EStepPlan& plan, const EStepArgs& args, const DeviceDocs& docs, cudaStream_t s) {
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3((unsigned) (docs.B * plan.cluster));
+	cfg.blockDim = dim3(ESTEP_THREADS);
+	cfg.dynamicSmemBytes = plan.smem;
+	cfg.stream = s;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeClusterDimension;
+	attr[0].val.clusterDim.x = plan.cluster;
+	attr[0].val.clusterDim.y = 1;
+	attr[0].val.clusterDim.z = 1;
+	cfg.attrs = attr;
+	cfg.numAttrs = CLUSTERED ? 1 : 0;
+	cudaLaunchKernelEx(&cfg, k_estep<T, CLUSTERED>, args, docs, plan.cluster, plan.kc, plan.n_cap, plan.n_fit);
+}
+
+void launch_estep(const EStepPlan& plan, const EStepArgs& args, const DeviceDocs& docs, int elem_size, cudaStream_t s) {
+	if(docs.B == 0)
+		return;
+	if(elem_size == 8) {
+		if(plan.cluster > 1) launch_estep_t<double, true>(plan, args, docs, s);
+		else launch_estep_t<double, false>(plan, args, docs, s);
+	} else {
+		if(plan.cluster > 1) launch_estep_t<float, true>(plan, args, docs, s);
+		else launch_estep_t<float, false>(plan, args, docs, s);
+	}
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// segmented scatter of the sufficient statistics (lda.cpp:207-217), optionally fused with the M-step blend
+// (onlinelda.cpp:99-100 / batchlda.cpp:60 / cumulativelda.cpp:69) and the next beta-prep (lda.cpp:172-173).
+//
+// Tokens are sorted by word once per minibatch; one CTA owns one word's K-vector, walks the word's tokens in
+// document order and accumulates weight_t * etheta[:, doc_t] in registers — no atomics, fixed summation order.
+// The K x B etheta matrix (65 MB at cfg-3) is L2-resident, so HBM sees lambda', lambda and beta once each.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int SCATTER_THREADS = 128;
+
+__device__ __forceinline__ double mstep_value(const MStepCoef& c, double lambda_prime, double s) {
+	if(c.mode == MSTEP_ONLINE) {
+		const double lambda_hat = c.eta + c.scale * s;                 // onlinelda.cpp:99
+		return (1. - c.rho) * lambda_prime + c.rho * lambda_hat;       // onlinelda.cpp:100
+	}
+	if(c.mode == MSTEP_BATCH)
+		return c.eta + s;                                              // batchlda.cpp:60
+	return lambda_prime + s;                                           // cumulativelda.cpp:69
+}
+
+template <typename TE, typename TB, int KPT>
+__global__ void __launch_bounds__(SCATTER_THREADS) k_scatter(ScatterArgs a, DeviceDocs docs) {
+	__shared__ double scratch[32];
+	const int K = a.K;
+	const TE* __restrict__ etheta = static_cast<const TE*>(a.etheta);
+	TB* beta = static_cast<TB*>(a.beta);
+	for(int w = blockIdx.x; w < a.V; w += gridDim.x) {
+		double acc[KPT];
+		#pragma unroll
+		for(int i = 0; i < KPT; ++i)
+			acc[i] = 0.0;
+		const int t0 = docs.word_ptr[w], t1 = docs.word_ptr[w + 1];
+		int t = t0;
+		for(; t + 4 <= t1; t += 4) {
+			int dd[4];
+			double ww[4];
+			#pragma unroll
+			for(int u = 0; u < 4; ++u) {
+				dd[u] = docs.tok_doc[t + u];
+				ww[u] = a.weight[docs.tok_src[t + u]];
+			}
+			TE v[4][KPT];
+			#pragma unroll
+			for(int u = 0; u < 4; ++u) {
+				const TE* col = etheta + (int64_t) dd[u] * K;
+				#pragma unroll
+				for(int i = 0; i < KPT; ++i) {
+					const int k = threadIdx.x + i * SCATTER_THREADS;
+					v[u][i] = k < K ? col[k] : TE(0);
+				}
+			}
+			#pragma unroll
+			for(int u = 0; u < 4; ++u)
+				#pragma unroll
+				for(int i = 0; i < KPT; ++i)
+					acc[i] = fma(ww[u], (double) v[u][i], acc[i]);
+		}
+		for(; t < t1; ++t) {
+			const int dd = docs.tok_doc[t];
+			const double ww = a.weight[docs.tok_src[t]];
+			const TE* col = etheta + (int64_t) dd * K;
+			#pragma unroll
+			for(int i = 0; i < KPT; ++i) {
+				const int k = threadIdx.x + i * SCATTER_THREADS;
+				if(k < K)
+					acc[i] = fma(ww, (double) col[k], acc[i]);
+			}
+		}
+
+		double psum = 0.0;
+		#pragma unroll
+		for(int i = 0; i < KPT; ++i) {
+			const int k = threadIdx.x + i * SCATTER_THREADS;
+			if(k >= K)
+				continue;
+			const int64_t e = (int64_t) w * K + k;
+			const double s = acc[i] * (double) beta[e];                  // lda.cpp:217
+			if(!a.fused) {
+				a.sstats[e] = s;
+				continue;
+			}
+			const double lp = a.coef.mode == MSTEP_BATCH ? 0.0 : a.lambda_prime[e];
+			const double lam = mstep_value(a.coef, lp, s);
+			a.lambda[e] = lam;
+			if(a.write_beta || a.psi_partials) {
+				const double p = digamma(lam);
+				psum += p;
+				if(a.write_beta)
+					beta[e] = (TB) exp(p - a.psi_rows[k]);
+			}
+		}
+		if(a.fused && a.psi_partials) {
+			const double total = block_sum(psum, scratch);
+			if(threadIdx.x == 0)
+				a.psi_partials[w] = total;
+		}
+	}
+}
+
+template <typename TE, typename TB>
+static void launch_scatter_t(const ScatterArgs& a, const DeviceDocs& docs, cudaStream_t s) {
+	const int grid = std::min(a.V, 148 * 64);
+	const int kpt = ceil_div(a.K, SCATTER_THREADS);
+	if(kpt <= 1) k_scatter<TE, TB, 1><<<grid, SCATTER_THREADS, 0, s>>>(a, docs);
+	else if(kpt <= 2) k_scatter<TE, TB, 2><<<grid, SCATTER_THREADS, 0, s>>>(a, docs);
+	else if(kpt <= 4) k_scatter<TE, TB, 4><<<grid, SCATTER_THREADS, 0, s>>>(a, docs);
+	else if(kpt <= 8) k_scatter<TE, TB, 8><<<grid, SCATTER_THREADS, 0, s>>>(a, docs);
+	else if(kpt <= 16) k_scatter<TE, TB, 16><<<grid, SCATTER_THREADS, 0, s>>>(a, docs);
+	else k_scatter<TE, TB, 32><<<grid, SCATTER_THREADS, 0, s>>>(a, docs);
+}
+
+void launch_scatter(const ScatterArgs& a, const DeviceDocs& docs, cudaStream_t s) {
+	if(a.etheta_elem == 8 && a.beta_elem == 8) launch_scatter_t<double, double>(a, docs, s);
+	else if(a.etheta_elem == 4 && a.beta_elem == 4) launch_scatter_t<float, float>(a, docs, s);
+	else if(a.etheta_elem == 8 && a.beta_elem == 4) launch_scatter_t<double, float>(a, docs, s);
+	else launch_scatter_t<float, double>(a, docs, s);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// dense M-step (after a cross-GPU exchange of sstats) + beta-prep
+// ------------------------------------------------------------------------------------------------------------
+template <typename TB>
+__global__ void __launch_bounds__(256) k_mstep(MStepArgs a) {
+	__shared__ double scratch[32];
+	TB* beta = static_cast<TB*>(a.beta);
+	for(int w = blockIdx.x; w < a.V; w += gridDim.x) {
+		double psum = 0.0;
+		for(int k = threadIdx.x; k < a.K; k += blockDim.x) {
+			const int64_t e = (int64_t) w * a.K + k;
+			const double lp = a.coef.mode == MSTEP_BATCH ? 0.0 : a.lambda_prime[e];
+			const double lam = mstep_value(a.coef, lp, a.sstats[e]);
+			a.lambda[e] = lam;
+			if(a.write_beta || a.psi_partials) {
+				const double p = digamma(lam);
+				psum += p;
+				if(a.write_beta)
+					beta[e] = (TB) exp(p - a.psi_rows[k]);
+			}
+		}
+		if(a.psi_partials) {
+			const double total = block_sum(psum, scratch);
+			if(threadIdx.x == 0)
+				a.psi_partials[w] = total;
+		}
+	}
+}
+
+void launch_mstep(const MStepArgs& a, cudaStream_t s) {
+	const int block = block_for_k(a.K);
+	const int grid = std::min(a.V, 148 * 16);
+	if(a.beta_elem == 8) k_mstep<double><<<grid, block, 0, s>>>(a);
+	else k_mstep<float><<<grid, block, 0, s>>>(a);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// phi = 1/K warm start (onlinelda.cpp:79-86) + beta-prep
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_wordcount(DeviceDocs docs, int V, double* __restrict__ wordcount) {
+	const int w = blockIdx.x * blockDim.x + threadIdx.x;
+	if(w >= V)
+		return;
+	double c = 0.0;
+	for(int t = docs.word_ptr[w]; t < docs.word_ptr[w + 1]; ++t)
+		c += docs.counts[docs.tok_src[t]];
+	wordcount[w] = c;
+}
+
+void launch_wordcount(const DeviceDocs& docs, int V, double* wordcount, cudaStream_t s) {
+	k_wordcount<<<ceil_div(V, 256), 256, 0, s>>>(docs, V, wordcount);
+}
+
+template <typename TB>
+__global__ void __launch_bounds__(256) k_init_update(int K, int V, double rho, double eta, double scale_k,
+                                                     const double* __restrict__ lambda_prime, double* __restrict__ lambda,
+                                                     const double* __restrict__ psi_rows, TB* __restrict__ beta,
+                                                     const double* __restrict__ wordcount) {
+	for(int w = blockIdx.x; w < V; w += gridDim.x) {
+		const double target = rho * (eta + scale_k * wordcount[w]);     // onlinelda.cpp:86
+		for(int k = threadIdx.x; k < K; k += blockDim.x) {
+			const int64_t e = (int64_t) w * K + k;
+			const double lam = (1. - rho) * lambda_prime[e] + target;   // onlinelda.cpp:85
+			lambda[e] = lam;
+			beta[e] = (TB) exp(digamma(lam) - psi_rows[k]);
+		}
+	}
+}
+
+void launch_init_update(const DeviceDocs& docs, int K, int V, double rho, double eta, double scale_k,
+                        const double* lambda_prime, double* lambda, const double* psi_rows, void* beta,
+                        int beta_elem, const double* wordcount, cudaStream_t s) {
+	const int block = block_for_k(K);
+	const int grid = std::min(V, 148 * 16);
+	if(beta_elem == 8)
+		k_init_update<double><<<grid, block, 0, s>>>(K, V, rho, eta, scale_k, lambda_prime, lambda, psi_rows,
+		                                              static_cast<double*>(beta), wordcount);
+	else
+		k_init_update<float><<<grid, block, 0, s>>>(K, V, rho, eta, scale_k, lambda_prime, lambda, psi_rows,
+		                                             static_cast<float*>(beta), wordcount);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// column sums over documents of a K x B matrix: out[k] = sum_d in[k + d*K]
+// ------------------------------------------------------------------------------------------------------------
+constexpr int COLSUM_CHUNK = 64;
+
+int colsum_num_partials(int64_t B) { return std::max(1, ceil_div(B, COLSUM_CHUNK)); }
+
+__global__ void __launch_bounds__(256) k_colsum_partial(const double* __restrict__ in, int K, int64_t B, double* __restrict__ partials) {
+	const int k = blockIdx.y * 256 + threadIdx.x;
+	if(k >= K)
+		return;
+	const int64_t d0 = (int64_t) blockIdx.x * COLSUM_CHUNK, d1 = min(B, d0 + COLSUM_CHUNK);
+	double acc = 0.0;
+	for(int64_t d = d0; d < d1; ++d)
+		acc += in[d * K + k];
+	partials[(int64_t) blockIdx.x * K + k] = acc;
+}
+
+void launch_colsum(const double* in, int K, int64_t B, double* partials, double* out, cudaStream_t s) {
+	const int P = colsum_num_partials(B);
+	k_colsum_partial<<<dim3(P, ceil_div(K, 256)), 256, 0, s>>>(in, K, B, partials);
+	k_reduce_partials<<<ceil_div(K, 256), 256, 0, s>>>(partials, P, K, out);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// alpha statistics: stat_dk = psi(gamma_dk) - psi(sum_k gamma_dk)   (onlinelda.cpp:124-128)
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_alpha_stats(const double* __restrict__ gamma, int K, int64_t B, double* __restrict__ stat) {
+	__shared__ double scratch[32];
+	for(int64_t d = blockIdx.x; d < B; d += gridDim.x) {
+		double local = 0.0;
+		for(int k = threadIdx.x; k < K; k += blockDim.x)
+			local += gamma[d * K + k];
+		const double psi_sum = digamma(block_sum(local, scratch));
+		for(int k = threadIdx.x; k < K; k += blockDim.x)
+			stat[d * K + k] = digamma(gamma[d * K + k]) - psi_sum;
+	}
+}
+
+void launch_alpha_stats(const double* gamma, int K, int64_t B, double* stat, cudaStream_t s) {
+	if(B == 0)
+		return;
+	k_alpha_stats<<<(unsigned) std::min<int64_t>(B, 148 * 16), block_for_k(K), 0, s>>>(gamma, K, B, stat);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Gamma(100, 1/100) generator for the initial gamma (lda.cpp:135) and lambda (lda.cpp:71).
+// Counter-based (Philox4x32-10 keyed by seed, counter = element index and draw number), Marsaglia–Tsang
+// rejection with Box–Muller normals: the value of element i depends only on (seed, stream, i).
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32(uint32_t c[4], uint32_t k0, uint32_t k1) {
+	#pragma unroll
+	for(int r = 0; r < 10; ++r) {
+		const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+		const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+		const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+		c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+		k0 += 0x9E3779B9u;
+		k1 += 0xBB67AE85u;
+	}
+}
+
+__global__ void __launch_bounds__(256) k_gamma_rng(double* __restrict__ out, int64_t n, uint64_t seed, uint64_t stream_id) {
+	const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= n)
+		return;
+	const double shape = 100.0;
+	const double dd = shape - 1.0 / 3.0, cc = 1.0 / sqrt(9.0 * dd);
+	double result = shape;
+	for(uint32_t attempt = 0; attempt < 64; ++attempt) {
+		uint32_t c[4] = {(uint32_t) i, (uint32_t) ((uint64_t) i >> 32), (uint32_t) stream_id, attempt};
+		philox4x32(c, (uint32_t) seed, (uint32_t) (seed >> 32));
+		// two uniforms in (0,1) with 32+21 bits, one more with 32 bits
+		const double u1 = ((double) c[0] + 0.5) * (1.0 / 4294967296.0);
+		const double u2 = ((double) c[1] + 0.5) * (1.0 / 4294967296.0);
+		const double u3 = ((double) c[2] + 0.5) * (1.0 / 4294967296.0);
+		const double x = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+		const double t = 1.0 + cc * x;
+		if(t <= 0.0)
+			continue;
+		const double v = t * t * t;
+		if(log(u3) < 0.5 * x * x + dd - dd * v + dd * log(v)) {
+			result = dd * v;
+			break;
+		}
+	}
+	out[i] = result / shape;
+}
+
+void launch_gamma_rng(double* out, int64_t n, uint64_t seed, uint64_t stream_id, cudaStream_t s) {
+	if(n > 0)
+		k_gamma_rng<<<(unsigned) ((n + 255) / 256), 256, 0, s>>>(out, n, seed, stream_id);
+}
+
+__global__ void k_fill(double* __restrict__ out, int64_t n, double v) {
+	const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	if(i < n)
+		out[i] = v;
+}
+
+void launch_fill(double* out, int64_t n, double value, cudaStream_t s) {
+	if(n > 0)
+		k_fill<<<(unsigned) ((n + 255) / 256), 256, 0, s>>>(out, n, value);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// deterministic sum of n doubles
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_sum_partial(const double* __restrict__ in, int64_t n, double* __restrict__ partials) {
+	__shared__ double scratch[32];
+	double acc = 0.0;
+	for(int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x)
+		acc += in[i];
+	const double total = block_sum(acc, scratch);
+	if(threadIdx.x == 0)
+		partials[blockIdx.x] = total;
+}
+
+__global__ void k_sum_final(const double* __restrict__ partials, int P, double* __restrict__ out) {
+	if(threadIdx.x == 0 && blockIdx.x == 0) {
+		double acc = 0.0;
+		for(int p = 0; p < P; ++p)
+			acc += partials[p];
+		out[0] = acc;
+	}
+}
+
+void launch_sum(const double* in, int64_t n, double* partials, double* out, cudaStream_t s) {
+	const int P = (int) std::max<int64_t>(1, std::min<int64_t>(1024, (n + 255) / 256));
+	k_sum_partial<<<P, 256, 0, s>>>(in, n, partials);
+	k_sum_final<<<1, 32, 0, s>>>(partials, P, out);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// adaptive learning rate state (onlinelda.cpp:167-175)
+// ------------------------------------------------------------------------------------------------------------
+int adaptive_num_blocks(int64_t n) { return (int) std::max<int64_t>(1, std::min<int64_t>(1024, (n + 255) / 256)); }
+
+__global__ void __launch_bounds__(256) k_adaptive(const double* __restrict__ sstats, const double* __restrict__ lambda_prime,
+                                                  double* __restrict__ grad, int64_t n, double eta, double scale, double tau,
+                                                  double* __restrict__ sq_partials) {
+	__shared__ double scratch[32];
+	double su = 0.0, sg = 0.0;
+	for(int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x) {
+		const double u = (eta + scale * sstats[i]) - lambda_prime[i];     // lambdaHat - lambdaPrime, :168
+		const double g = (1. - 1. / tau) * grad[i] + 1. / tau * u;        // :171
+		grad[i] = g;
+		su += u * u;
+		sg += g * g;
+	}
+	const double tu = block_sum(su, scratch);
+	const double tg = block_sum(sg, scratch);
+	if(threadIdx.x == 0) {
+		sq_partials[blockIdx.x] = tu;
+		sq_partials[gridDim.x + blockIdx.x] = tg;
+	}
+}
+
+void launch_adaptive(const double* sstats, const double* lambda_prime, double* grad, int64_t n, double eta,
+                     double scale, double tau, double* sq_partials, cudaStream_t s) {
+	k_adaptive<<<adaptive_num_blocks(n), 256, 0, s>>>(sstats, lambda_prime, grad, n, eta, scale, tau, sq_partials);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// variational lower bound (intended formula; see include/trlda_b200.h)
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_elbo_docs(DeviceDocs docs, int K, const double* __restrict__ lambda,
+                                                   const double* __restrict__ psi_rows, const double* __restrict__ alpha,
+                                                   double alpha_const, const double* __restrict__ gamma, double* __restrict__ per_doc) {
+	extern __shared__ double elogtheta[];   // K
+	__shared__ double scratch[32];
+	for(int64_t d = blockIdx.x; d < docs.B; d += gridDim.x) {
+		const double* g = gamma + d * K;
+		double local = 0.0;
+		for(int k = threadIdx.x; k < K; k += blockDim.x)
+			local += g[k];
+		const double gsum = block_sum(local, scratch);
+		const double psi_gsum = digamma(gsum);
+		double score = 0.0;
+		for(int k = threadIdx.x; k < K; k += blockDim.x) {
+			const double e = digamma(g[k]) - psi_gsum;                   // lda.cpp:341
+			elogtheta[k] = e;
+			score += (alpha[k] - g[k]) * e + lgamma(g[k]);               // lda.cpp:349-351
+		}
+		__syncthreads();
+		for(int64_t j = docs.doc_ptr[d]; j < docs.doc_ptr[d + 1]; ++j) {
+			const double* col = lambda + (int64_t) docs.word_ids[j] * K;
+			// log sum_k exp(Elogtheta_k + Elogbeta_kw), max-subtracted (onlineldavb.py:289-296)
+			double tmax = -CUDART_INF;
+			for(int k = threadIdx.x; k < K; k += blockDim.x)
+				tmax = fmax(tmax, elogtheta[k] + digamma(col[k]) - psi_rows[k]);
+			#pragma unroll
+			for(int o = 16; o > 0; o >>= 1)
+				tmax = fmax(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+			__syncthreads();
+			if((threadIdx.x & 31) == 0)
+				scratch[threadIdx.x >> 5] = tmax;
+			__syncthreads();
+			for(int i = 0; i < (int) ((blockDim.x + 31) >> 5); ++i)
+				tmax = fmax(tmax, scratch[i]);
+			double sum = 0.0;
+			for(int k = threadIdx.x; k < K; k += blockDim.x)
+				sum += exp(elogtheta[k] + digamma(col[k]) - psi_rows[k] - tmax);
+			sum = block_sum(sum, scratch);
+			if(threadIdx.x == 0)
+				score += docs.counts[j] * (log(sum) + tmax);
+		}
+		score = block_sum(score, scratch);
+		if(threadIdx.x == 0)
+			per_doc[d] = score - lgamma(gsum) + alpha_const;
+		__syncthreads();
+	}
+}
+
+void launch_elbo_docs(const DeviceDocs& docs, int K, const double* lambda, const double* psi_rows,
+                      const double* alpha, double alpha_const, const double* gamma, double* per_doc, cudaStream_t s) {
+	if(docs.B == 0)
+		return;
+	k_elbo_docs<<<(unsigned) std::min<int64_t>(docs.B, 148 * 8), block_for_k(K), (size_t) K * 8, s>>>(
+		docs, K, lambda, psi_rows, alpha, alpha_const, gamma, per_doc);
+}
+
+__global__ void __launch_bounds__(256) k_elbo_beta(const double* __restrict__ lambda, const double* __restrict__ psi_rows,
+                                                   int K, int V, double eta, double* __restrict__ partial) {
+	__shared__ double scratch[32];
+	for(int w = blockIdx.x; w < V; w += gridDim.x) {
+		double acc = 0.0;
+		for(int k = threadIdx.x; k < K; k += blockDim.x) {
+			const double l = lambda[(int64_t) w * K + k];
+			acc += (eta - l) * (digamma(l) - psi_rows[k]) + lgamma(l);   // lda.cpp:317 (beta part), :357
+		}
+		const double total = block_sum(acc, scratch);
+		if(threadIdx.x == 0)
+			partial[w] = total;
+	}
+}
+
+void launch_elbo_beta(const double* lambda, const double* psi_rows, int K, int V, double eta, double* partial,
+                      cudaStream_t s) {
+	k_elbo_beta<<<std::min(V, 148 * 16), block_for_k(K), 0, s>>>(lambda, psi_rows, K, V, eta, partial);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// special-function test hook
+// ------------------------------------------------------------------------------------------------------------
+__global__ void k_special(int which, const double* __restrict__ x, int64_t n, double* __restrict__ out) {
+	const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= n)
+		return;
+	const double v = x[i];
+	double r;
+	switch(which) {
+		case 0: r = digamma(v); break;
+		case 1: r = trigamma(v); break;
+		case 2: r = lgamma(v); break;
+		default: r = (double) exp_digamma_f32((float) v); break;
+	}
+	out[i] = r;
+}
+
+void launch_special(int which, const double* x, int64_t n, double* out, cudaStream_t s) {
+	if(n > 0)
+		k_special<<<(unsigned) ((n + 127) / 128), 128, 0, s>>>(which, x, n, out);
+}
+
+}  // namespace trlda

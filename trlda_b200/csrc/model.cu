@@ -1,0 +1,1530 @@
+// model.cu — host side of the C ABI (include/trlda_b200.h): model state in HBM, the three updateParameters
+// drivers, minibatch upload, multi-GPU exchange and instrumentation.  Everything numerical runs in the kernels
+// of kernels.cu; the host only sequences launches and does the K-vector / scalar Newton steps of the
+// empirical-Bayes updates.  Reference citations are relative to /root/reference/code/trlda/.
+#include "../../include/trlda_b200.h"
+#include "kernels.cuh"
+#include "special.cuh"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace trlda;
+
+// ------------------------------------------------------------------------------------------------------------
+// small utilities
+// ------------------------------------------------------------------------------------------------------------
+namespace {
+
+thread_local std::string g_error;
+std::mutex g_seed_mutex;
+uint64_t g_seed = 0x5DEECE66DULL;
+uint64_t g_stream_counter = 0;
+
+uint64_t next_stream_id() {
+	std::lock_guard<std::mutex> lock(g_seed_mutex);
+	return ++g_stream_counter;
+}
+
+uint64_t current_seed() {
+	std::lock_guard<std::mutex> lock(g_seed_mutex);
+	return g_seed;
+}
+
+struct DevBuf {
+	void* p = nullptr;
+	size_t cap = 0;
+	cudaError_t ensure(size_t bytes) {
+		if(bytes <= cap)
+			return cudaSuccess;
+		if(p)
+			cudaFree(p);
+		p = nullptr;
+		cap = 0;
+		// grow geometrically for the per-minibatch buffers, exact for the big K x V ones
+		size_t want = bytes < (64u << 20) ? bytes + bytes / 4 + 256 : bytes;
+		cudaError_t e = cudaMalloc(&p, want);
+		if(e == cudaSuccess)
+			cap = want;
+		return e;
+	}
+	void release() {
+		if(p)
+			cudaFree(p);
+		p = nullptr;
+		cap = 0;
+	}
+	template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
+struct PinnedBuf {
+	void* p = nullptr;
+	size_t cap = 0;
+	cudaError_t ensure(size_t bytes) {
+		if(bytes <= cap)
+			return cudaSuccess;
+		if(p)
+			cudaFreeHost(p);
+		p = nullptr;
+		cap = 0;
+		size_t want = bytes + bytes / 4 + 256;
+		cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+		if(e == cudaSuccess)
+			cap = want;
+		return e;
+	}
+	void release() {
+		if(p)
+			cudaFreeHost(p);
+		p = nullptr;
+		cap = 0;
+	}
+	template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
+// ---- NCCL through dlopen: no link-time dependency, only needed once trlda_comm_init is called -------------------
+struct NcclApi {
+	void* handle = nullptr;
+	ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+	ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+	ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+	const char* (*GetErrorString)(ncclResult_t) = nullptr;
+	bool ok = false;
+};
+
+NcclApi& nccl_api() {
+	static NcclApi api;
+	static std::once_flag once;
+	std::call_once(once, [] {
+		const char* names[] = {"libnccl.so.2", "libnccl.so"};
+		for(const char* name : names) {
+			api.handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+			if(api.handle)
+				break;
+		}
+		if(!api.handle)
+			return;
+		api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(api.handle, "ncclGetUniqueId"));
+		api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(api.handle, "ncclCommInitRank"));
+		api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(api.handle, "ncclCommDestroy"));
+		api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(api.handle, "ncclAllReduce"));
+		api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(api.handle, "ncclGetErrorString"));
+		api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.GetErrorString;
+	});
+	return api;
+}
+
+// ---- host special functions for the Newton steps ----------------------------------------------------------------
+
+// Hurwitz zeta(s, q) for s > 1, q > 0 by Euler–Maclaurin summation (what zeta.cpp:67-134 computes): direct
+// terms up to a = q + N, then the integral, half-term and Bernoulli corrections.
+double hurwitz_zeta(double s, double q) {
+	if(!(s > 1.0) || !(q > 0.0))
+		return NAN;
+	static const double B2k[] = {1.0 / 6, -1.0 / 30, 1.0 / 42, -1.0 / 30, 5.0 / 66, -691.0 / 2730, 7.0 / 6,
+	                             -3617.0 / 510, 43867.0 / 798, -174611.0 / 330};
+	if(q > 1e8)
+		return (1.0 / (s - 1.0) + 1.0 / (2.0 * q)) * pow(q, 1.0 - s);     // leading asymptotic terms, as zeta.cpp:98-100
+	double sum = 0.0, a = q;
+	for(int i = 0; i < 10 || a < 12.0; ++i) {
+		sum += pow(a, -s);
+		a += 1.0;
+	}
+	sum += pow(a, 1.0 - s) / (s - 1.0) + 0.5 * pow(a, -s);
+	double fact = 1.0, poch = s, apow = pow(a, -s - 1.0);   // s (s+1) ... / (2k)! * a^(-s-2k+1)
+	for(int k = 0; k < 10; ++k) {
+		fact *= (2.0 * k + 1.0) * (2.0 * k + 2.0);
+		const double term = B2k[k] * poch / fact * apow;
+		sum += term;
+		if(fabs(term) < 1e-17 * fabs(sum))
+			break;
+		poch *= (s + 2.0 * k + 1.0) * (s + 2.0 * k + 2.0);
+		apow /= a * a;
+	}
+	return sum;
+}
+
+double host_polygamma(int n, double x) {
+	if(n < 1)
+		return digamma(x);
+	if(n == 1 && x > 0.0)
+		return trigamma(x);
+	return pow(-1.0, n + 1) * tgamma(n + 1.0) * hurwitz_zeta(n + 1.0, x);   // utils.cpp:107-111
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------------
+// the model
+// ------------------------------------------------------------------------------------------------------------
+struct trlda_model {
+	int kind = 0, K = 0, V = 0, device = 0, precision = TRLDA_PRECISION_FP64;
+	int64_t num_documents = 0, update_count = 0;
+	double eta = .3;
+	std::vector<double> alpha;
+
+	// adaptive learning rate (onlinelda.h:41-44)
+	double ada_rho = 1. / 1000., ada_tau = 1000., ada_sq_norm = 1.;
+	DevBuf ada_gradient;
+	// cumulative alpha statistics (cumulativelda.h:24-25)
+	std::vector<double> psi_gamma_diff;
+	int64_t cum_num_documents = 0;
+
+	cudaStream_t stream = nullptr;
+	int smem_optin = 0, num_sms = 0;
+	int force_cluster = 0;
+
+	// K x V state: lambda lives in lam[cur]; the other buffer receives the next lambda (lambda' = old buffer)
+	DevBuf lam[2];
+	int cur = 0;
+	DevBuf beta;            // expElogbeta, element size beta_elem
+	int beta_elem = 8;
+	bool beta_valid = false;
+	DevBuf sstats;
+	DevBuf rows, rows_prev, rows_stat, psi_rows, d_alpha, partials, vpartials, scalars;
+
+	// minibatch
+	DeviceDocs docs;
+	DevBuf b_doc_ptr, b_word_ids, b_counts, b_word_ptr, b_tok_doc, b_tok_src, wordcount;
+	PinnedBuf staging, readback;
+	int64_t docs_total_count = 0;    // sum of all counts in the (global) minibatch
+	int64_t global_B = 0;            // documents over all ranks
+	bool docs_resident = false;
+
+	// per-minibatch E-step buffers
+	DevBuf gamma, etheta, etheta32, weight, doc_stat, iterations;
+	bool gamma_valid = false;
+
+	// parity seams
+	std::vector<double> inj_gamma;
+	int64_t inj_gamma_cols = -1;
+	std::vector<double> inj_lambda;
+
+	// multi-GPU
+	ncclComm_t comm = nullptr;
+	int rank = 0, nranks = 1;
+
+	// instrumentation
+	bool profiling = false;
+	struct Span { int kind; cudaEvent_t a, b; };
+	std::vector<Span> spans;
+	std::vector<cudaEvent_t> event_pool;
+	trlda_stats stats{};
+
+	std::string error;
+
+	double* lambda() { return lam[cur].as<double>(); }
+	double* lambda_next() { return lam[1 - cur].as<double>(); }
+};
+
+namespace {
+
+int fail(trlda_model* m, int code, const std::string& msg) {
+	if(m)
+		m->error = msg;
+	g_error = msg;
+	return code;
+}
+
+#define CUDA_TRY(m, expr)                                                                              \
+	do {                                                                                               \
+		cudaError_t e__ = (expr);                                                                      \
+		if(e__ != cudaSuccess)                                                                         \
+			return fail(m, TRLDA_ERR_CUDA, std::string("CUDA error: ") + cudaGetErrorString(e__) + " at " #expr); \
+	} while(0)
+
+#define TRY(expr)                  \
+	do {                           \
+		int s__ = (expr);          \
+		if(s__ != TRLDA_OK)        \
+			return s__;            \
+	} while(0)
+
+#define NCCL_TRY(m, expr)                                                                                   \
+	do {                                                                                                    \
+		ncclResult_t r__ = (expr);                                                                          \
+		if(r__ != ncclSuccess)                                                                              \
+			return fail(m, TRLDA_ERR_CUDA, std::string("NCCL error: ") + nccl_api().GetErrorString(r__));  \
+	} while(0)
+
+// brackets one kernel launch for the timing table
+struct Launch {
+	trlda_model* m;
+	int kind;
+	cudaEvent_t a = nullptr, b = nullptr;
+	Launch(trlda_model* m_, int kind_) : m(m_), kind(kind_) {
+		m->stats.launches[kind]++;
+		m->stats.total_launches++;
+		if(m->profiling) {
+			a = take();
+			b = take();
+			cudaEventRecord(a, m->stream);
+		}
+	}
+	~Launch() {
+		if(m->profiling) {
+			cudaEventRecord(b, m->stream);
+			m->spans.push_back({kind, a, b});
+		}
+	}
+	cudaEvent_t take() {
+		if(!m->event_pool.empty()) {
+			cudaEvent_t e = m->event_pool.back();
+			m->event_pool.pop_back();
+			return e;
+		}
+		cudaEvent_t e;
+		cudaEventCreate(&e);
+		return e;
+	}
+};
+
+int check_launch(trlda_model* m, const char* what) {
+	cudaError_t e = cudaGetLastError();
+	if(e != cudaSuccess)
+		return fail(m, TRLDA_ERR_CUDA, std::string("CUDA launch failed (") + what + "): " + cudaGetErrorString(e));
+	return TRLDA_OK;
+}
+
+int set_device(trlda_model* m) {
+	CUDA_TRY(m, cudaSetDevice(m->device));
+	return TRLDA_OK;
+}
+
+size_t kv_bytes(const trlda_model* m) { return (size_t) m->K * m->V * sizeof(double); }
+
+int ensure_beta(trlda_model* m) {
+	const int elem = m->precision == TRLDA_PRECISION_MIXED ? 4 : 8;
+	if(elem != m->beta_elem) {
+		m->beta_elem = elem;
+		m->beta_valid = false;
+	}
+	CUDA_TRY(m, m->beta.ensure((size_t) m->K * m->V * elem));
+	return TRLDA_OK;
+}
+
+int upload_alpha(trlda_model* m) {
+	CUDA_TRY(m, m->d_alpha.ensure(sizeof(double) * m->K));
+	CUDA_TRY(m, cudaMemcpyAsync(m->d_alpha.p, m->alpha.data(), sizeof(double) * m->K, cudaMemcpyHostToDevice, m->stream));
+	CUDA_TRY(m, cudaStreamSynchronize(m->stream));   // alpha.data() may be reallocated by the caller later
+	m->stats.h2d_bytes += sizeof(double) * m->K;
+	return TRLDA_OK;
+}
+
+// sum over ranks, in place, on the model's stream
+int allreduce(trlda_model* m, void* buf, size_t count, ncclDataType_t type) {
+	if(m->nranks <= 1)
+		return TRLDA_OK;
+	NCCL_TRY(m, nccl_api().AllReduce(buf, buf, count, type, ncclSum, m->comm, m->stream));
+	return TRLDA_OK;
+}
+
+// rows = row sums of `matrix`
+int compute_rows(trlda_model* m, const double* matrix, double* out) {
+	int P = rowsum_num_partials(m->V);
+	CUDA_TRY(m, m->partials.ensure(sizeof(double) * (size_t) std::max(P, colsum_num_partials(std::max<int64_t>(m->docs.B, 1))) * m->K));
+	{
+		Launch l(m, KK_ROWSUM);
+		launch_rowsum(matrix, m->K, m->V, m->partials.as<double>(), &P, m->stream);
+	}
+	{
+		Launch l(m, KK_REDUCE);
+		launch_reduce_partials(m->partials.as<double>(), P, m->K, out, m->stream);
+	}
+	return check_launch(m, "rowsum");
+}
+
+int ensure_small(trlda_model* m) {
+	CUDA_TRY(m, m->rows.ensure(sizeof(double) * m->K));
+	CUDA_TRY(m, m->rows_prev.ensure(sizeof(double) * m->K));
+	CUDA_TRY(m, m->rows_stat.ensure(sizeof(double) * m->K));
+	CUDA_TRY(m, m->psi_rows.ensure(sizeof(double) * m->K));
+	CUDA_TRY(m, m->vpartials.ensure(sizeof(double) * std::max(m->V, 2048)));
+	CUDA_TRY(m, m->scalars.ensure(sizeof(double) * 4096));
+	CUDA_TRY(m, m->readback.ensure(sizeof(double) * (size_t) std::max(m->K, 4096)));
+	return TRLDA_OK;
+}
+
+// beta = exp(psi(lambda) - psi(rowsum lambda)) for the CURRENT lambda (lda.cpp:172-173)
+int prepare_beta(trlda_model* m, bool want_psi_partials = false) {
+	TRY(ensure_beta(m));
+	TRY(ensure_small(m));
+	if(m->beta_valid && !want_psi_partials)
+		return TRLDA_OK;
+	TRY(compute_rows(m, m->lambda(), m->rows.as<double>()));
+	{
+		Launch l(m, KK_MISC);
+		launch_psi_vector(m->rows.as<double>(), m->K, m->psi_rows.as<double>(), m->stream);
+	}
+	{
+		Launch l(m, KK_BETA_PREP);
+		launch_beta_prep(m->lambda(), m->psi_rows.as<double>(), m->K, m->V, m->beta.p, m->beta_elem,
+		                 want_psi_partials ? m->vpartials.as<double>() : nullptr, m->stream);
+	}
+	m->beta_valid = true;
+	return check_launch(m, "beta_prep");
+}
+
+// ---- minibatch upload: CSR + word-sorted token list ---------------------------------------------------------------
+int upload_docs(trlda_model* m, const trlda_docs* docs) {
+	TRY(set_device(m));
+	if(!docs || docs->num_docs < 0 || (docs->num_docs > 0 && !docs->doc_ptr))
+		return fail(m, TRLDA_ERR_ARG, "Documents must be given in CSR form.");
+	const int64_t B = docs->num_docs;
+	const int64_t N = B ? docs->doc_ptr[B] : 0;
+	const int V = m->V;
+	if(N > INT32_MAX)
+		return fail(m, TRLDA_ERR_ARG, "Too many (word, count) pairs in one minibatch.");
+
+	// pinned staging: [doc_ptr | word_ids | counts | word_ptr | tok_doc | tok_src]
+	const size_t o_ptr = 0;
+	const size_t o_ids = o_ptr + sizeof(int64_t) * (B + 1);
+	const size_t o_cts = o_ids + sizeof(int32_t) * N;
+	const size_t o_wptr = o_cts + sizeof(int32_t) * N;
+	const size_t o_tdoc = o_wptr + sizeof(int32_t) * ((size_t) V + 1);
+	const size_t o_tsrc = o_tdoc + sizeof(int32_t) * N;
+	const size_t total = o_tsrc + sizeof(int32_t) * N;
+	CUDA_TRY(m, m->staging.ensure(total));
+	char* base = m->staging.as<char>();
+	int64_t* s_ptr = reinterpret_cast<int64_t*>(base + o_ptr);
+	int32_t* s_ids = reinterpret_cast<int32_t*>(base + o_ids);
+	int32_t* s_cts = reinterpret_cast<int32_t*>(base + o_cts);
+	int32_t* s_wptr = reinterpret_cast<int32_t*>(base + o_wptr);
+	int32_t* s_tdoc = reinterpret_cast<int32_t*>(base + o_tdoc);
+	int32_t* s_tsrc = reinterpret_cast<int32_t*>(base + o_tsrc);
+
+	// make sure the previous use of the staging buffer has been consumed
+	CUDA_TRY(m, cudaStreamSynchronize(m->stream));
+
+	if(B)
+		memcpy(s_ptr, docs->doc_ptr, sizeof(int64_t) * (B + 1));
+	else
+		s_ptr[0] = 0;
+	if(N) {
+		memcpy(s_ids, docs->word_ids, sizeof(int32_t) * N);
+		memcpy(s_cts, docs->counts, sizeof(int32_t) * N);
+	}
+	int n_max = 0;
+	int64_t total_count = 0;
+	for(int64_t d = 0; d < B; ++d) {
+		const int64_t n = s_ptr[d + 1] - s_ptr[d];
+		if(n < 0)
+			return fail(m, TRLDA_ERR_ARG, "Document offsets must be non-decreasing.");
+		n_max = std::max<int64_t>(n_max, n);
+	}
+	// stable counting sort of the tokens by word id
+	memset(s_wptr, 0, sizeof(int32_t) * ((size_t) V + 1));
+	for(int64_t t = 0; t < N; ++t) {
+		const int32_t w = s_ids[t];
+		if(w < 0 || w >= V)
+			return fail(m, TRLDA_ERR_ARG, "Word ID out of range.");
+		s_wptr[w + 1]++;
+		total_count += s_cts[t];
+	}
+	for(int w = 0; w < V; ++w)
+		s_wptr[w + 1] += s_wptr[w];
+	{
+		std::vector<int32_t> cursor(s_wptr, s_wptr + V);
+		for(int64_t d = 0; d < B; ++d)
+			for(int64_t t = s_ptr[d]; t < s_ptr[d + 1]; ++t) {
+				const int32_t pos = cursor[s_ids[t]]++;
+				s_tdoc[pos] = (int32_t) d;
+				s_tsrc[pos] = (int32_t) t;
+			}
+	}
+
+	CUDA_TRY(m, m->b_doc_ptr.ensure(sizeof(int64_t) * (B + 1)));
+	CUDA_TRY(m, m->b_word_ids.ensure(sizeof(int32_t) * std::max<int64_t>(N, 1)));
+	CUDA_TRY(m, m->b_counts.ensure(sizeof(int32_t) * std::max<int64_t>(N, 1)));
+	CUDA_TRY(m, m->b_word_ptr.ensure(sizeof(int32_t) * ((size_t) V + 1)));
+	CUDA_TRY(m, m->b_tok_doc.ensure(sizeof(int32_t) * std::max<int64_t>(N, 1)));
+	CUDA_TRY(m, m->b_tok_src.ensure(sizeof(int32_t) * std::max<int64_t>(N, 1)));
+	CUDA_TRY(m, cudaMemcpyAsync(m->b_doc_ptr.p, s_ptr, sizeof(int64_t) * (B + 1), cudaMemcpyHostToDevice, m->stream));
+	if(N) {
+		CUDA_TRY(m, cudaMemcpyAsync(m->b_word_ids.p, s_ids, sizeof(int32_t) * N, cudaMemcpyHostToDevice, m->stream));
+		CUDA_TRY(m, cudaMemcpyAsync(m->b_counts.p, s_cts, sizeof(int32_t) * N, cudaMemcpyHostToDevice, m->stream));
+		CUDA_TRY(m, cudaMemcpyAsync(m->b_tok_doc.p, s_tdoc, sizeof(int32_t) * N, cudaMemcpyHostToDevice, m->stream));
+		CUDA_TRY(m, cudaMemcpyAsync(m->b_tok_src.p, s_tsrc, sizeof(int32_t) * N, cudaMemcpyHostToDevice, m->stream));
+	}
+	CUDA_TRY(m, cudaMemcpyAsync(m->b_word_ptr.p, s_wptr, sizeof(int32_t) * ((size_t) V + 1), cudaMemcpyHostToDevice, m->stream));
+	m->stats.h2d_bytes += total;
+
+	m->docs.B = B;
+	m->docs.N = N;
+	m->docs.n_max = n_max;
+	m->docs.doc_ptr = m->b_doc_ptr.as<int64_t>();
+	m->docs.word_ids = m->b_word_ids.as<int32_t>();
+	m->docs.counts = m->b_counts.as<int32_t>();
+	m->docs.word_ptr = m->b_word_ptr.as<int32_t>();
+	m->docs.tok_doc = m->b_tok_doc.as<int32_t>();
+	m->docs.tok_src = m->b_tok_src.as<int32_t>();
+	m->docs_total_count = total_count;
+	m->global_B = B;
+	m->gamma_valid = false;
+	m->docs_resident = true;
+
+	if(m->nranks > 1) {
+		// batch-wide document count and token count
+		TRY(ensure_small(m));
+		int64_t* h = m->readback.as<int64_t>();
+		h[0] = B;
+		h[1] = total_count;
+		CUDA_TRY(m, cudaMemcpyAsync(m->scalars.p, h, 2 * sizeof(int64_t), cudaMemcpyHostToDevice, m->stream));
+		TRY(allreduce(m, m->scalars.p, 2, ncclInt64));
+		CUDA_TRY(m, cudaMemcpyAsync(h, m->scalars.p, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, m->stream));
+		CUDA_TRY(m, cudaStreamSynchronize(m->stream));
+		m->global_B = h[0];
+		m->docs_total_count = h[1];
+	}
+
+	// per-minibatch buffers
+	const size_t kb = sizeof(double) * (size_t) m->K * std::max<int64_t>(B, 1);
+	CUDA_TRY(m, m->gamma.ensure(kb));
+	CUDA_TRY(m, m->etheta.ensure(kb));
+	CUDA_TRY(m, m->etheta32.ensure(kb / 2));
+	CUDA_TRY(m, m->doc_stat.ensure(kb));
+	CUDA_TRY(m, m->weight.ensure(sizeof(double) * std::max<int64_t>(N, 1)));
+	CUDA_TRY(m, m->iterations.ensure(sizeof(int32_t) * std::max<int64_t>(B, 1)));
+	return TRLDA_OK;
+}
+
+// where the initial gamma of an E-step comes from
+enum GammaSource { GAMMA_FRESH, GAMMA_KEEP, GAMMA_HOST };
+
+// fresh gamma: injected values if the parity seam is armed, else Gamma(100, 1/100) from the device generator
+int fresh_gamma(trlda_model* m) {
+	const int64_t B = m->docs.B;
+	if(m->inj_gamma_cols >= 0) {
+		if(m->inj_gamma_cols != B)
+			return fail(m, TRLDA_ERR_ARG, "Initial gamma has wrong dimensionality.");
+		if(B) {
+			CUDA_TRY(m, cudaMemcpyAsync(m->gamma.p, m->inj_gamma.data(), sizeof(double) * (size_t) m->K * B,
+			                            cudaMemcpyHostToDevice, m->stream));
+			m->stats.h2d_bytes += sizeof(double) * (size_t) m->K * B;
+		}
+		return TRLDA_OK;
+	}
+	Launch l(m, KK_RNG);
+	launch_gamma_rng(m->gamma.as<double>(), (int64_t) m->K * B, current_seed(), next_stream_id(), m->stream);
+	return check_launch(m, "gamma_rng");
+}
+
+// LDA::updateVariablesVI without the scatter: gamma fixed point for every document of the resident minibatch
+int run_estep(trlda_model* m, GammaSource src, const double* host_gamma, int max_iter, double threshold) {
+	if(src == GAMMA_FRESH)
+		TRY(fresh_gamma(m));
+	else if(src == GAMMA_HOST && m->docs.B) {
+		CUDA_TRY(m, cudaMemcpyAsync(m->gamma.p, host_gamma, sizeof(double) * (size_t) m->K * m->docs.B,
+		                            cudaMemcpyHostToDevice, m->stream));
+		m->stats.h2d_bytes += sizeof(double) * (size_t) m->K * m->docs.B;
+	}
+	const EStepPlan plan = plan_estep(m->K, m->docs.n_max, m->beta_elem, m->smem_optin, m->force_cluster);
+	if(plan.n_cap < m->docs.n_max || plan.smem > (size_t) m->smem_optin)
+		return fail(m, TRLDA_ERR_UNSUPPORTED, "A document has too many distinct words for the E-step kernel.");
+	EStepArgs a;
+	a.K = m->K;
+	a.beta = m->beta.p;
+	a.alpha = m->d_alpha.as<double>();
+	a.gamma = m->gamma.as<double>();
+	a.etheta = m->etheta.as<double>();
+	a.etheta32 = m->beta_elem == 4 ? m->etheta32.as<float>() : nullptr;
+	a.weight = m->weight.as<double>();
+	a.doc_stat = m->doc_stat.as<double>();
+	a.iterations = m->iterations.as<int32_t>();
+	a.max_iter = max_iter;
+	a.threshold = threshold;
+	{
+		Launch l(m, KK_ESTEP);
+		launch_estep(plan, a, m->docs, m->beta_elem, m->stream);
+	}
+	m->gamma_valid = true;
+	m->stats.estep_docs = m->docs.B;
+	return check_launch(m, "estep");
+}
+
+// row sums of the sufficient statistics of the last E-step (summed over ranks) -> rows_stat
+int reduce_doc_stat(trlda_model* m) {
+	const int P = colsum_num_partials(m->docs.B);
+	CUDA_TRY(m, m->partials.ensure(sizeof(double) * (size_t) std::max(P, rowsum_num_partials(m->V)) * m->K));
+	{
+		Launch l(m, KK_REDUCE);
+		launch_colsum(m->doc_stat.as<double>(), m->K, m->docs.B, m->partials.as<double>(), m->rows_stat.as<double>(), m->stream);
+	}
+	TRY(check_launch(m, "colsum"));
+	return allreduce(m, m->rows_stat.p, m->K, ncclDouble);
+}
+
+// dense sufficient statistics of the last E-step (summed over ranks) -> sstats   (lda.cpp:207-217)
+int run_scatter_dense(trlda_model* m) {
+	CUDA_TRY(m, m->sstats.ensure(kv_bytes(m)));
+	ScatterArgs a;
+	a.K = m->K;
+	a.V = m->V;
+	a.etheta = m->beta_elem == 4 ? m->etheta32.p : m->etheta.p;
+	a.etheta_elem = m->beta_elem == 4 ? 4 : 8;
+	a.weight = m->weight.as<double>();
+	a.beta = m->beta.p;
+	a.beta_elem = m->beta_elem;
+	a.sstats = m->sstats.as<double>();
+	a.fused = false;
+	{
+		Launch l(m, KK_SCATTER);
+		launch_scatter(a, m->docs, m->stream);
+	}
+	TRY(check_launch(m, "scatter"));
+	return allreduce(m, m->sstats.p, (size_t) m->K * m->V, ncclDouble);
+}
+
+// M-step: rebuild lambda from the last E-step.  lambda' is the CURRENT buffer unless `prime` is given; the new
+// lambda goes to the other buffer and becomes current.  Also refreshes rows / psi_rows (by linearity of the
+// blend) and, if asked, beta and the per-word psi sums for the eta update.
+int run_mstep(trlda_model* m, const MStepCoef& coef, const double* prime, double* target, bool write_beta,
+              bool want_psi_partials, bool force_dense) {
+	TRY(reduce_doc_stat(m));
+	double a = 0, b = 0, c = 0;
+	if(coef.mode == MSTEP_ONLINE) {
+		a = 1. - coef.rho;
+		b = coef.rho * m->V * coef.eta;
+		c = coef.rho * coef.scale;
+	} else if(coef.mode == MSTEP_BATCH) {
+		a = 0.;
+		b = m->V * coef.eta;
+		c = 1.;
+	} else {
+		a = 1.;
+		b = 0.;
+		c = 1.;
+	}
+	{
+		Launch l(m, KK_MISC);
+		launch_rows_update(coef.mode == MSTEP_BATCH ? nullptr : m->rows_prev.as<double>(), m->rows_stat.as<double>(), a, b, c,
+		                   m->K, m->rows.as<double>(), m->psi_rows.as<double>(), m->stream);
+	}
+	const bool dense = force_dense || m->nranks > 1;
+	if(dense) {
+		TRY(run_scatter_dense(m));
+		MStepArgs ma;
+		ma.K = m->K;
+		ma.V = m->V;
+		ma.coef = coef;
+		ma.sstats = m->sstats.as<double>();
+		ma.lambda_prime = prime;
+		ma.lambda = target;
+		ma.psi_rows = m->psi_rows.as<double>();
+		ma.beta = m->beta.p;
+		ma.beta_elem = m->beta_elem;
+		ma.write_beta = write_beta;
+		ma.psi_partials = want_psi_partials ? m->vpartials.as<double>() : nullptr;
+		Launch l(m, KK_MSTEP);
+		launch_mstep(ma, m->stream);
+	} else {
+		ScatterArgs sa;
+		sa.K = m->K;
+		sa.V = m->V;
+		sa.etheta = m->beta_elem == 4 ? m->etheta32.p : m->etheta.p;
+		sa.etheta_elem = m->beta_elem == 4 ? 4 : 8;
+		sa.weight = m->weight.as<double>();
+		sa.beta = m->beta.p;
+		sa.beta_elem = m->beta_elem;
+		sa.fused = true;
+		sa.coef = coef;
+		sa.lambda_prime = prime;
+		sa.lambda = target;
+		sa.psi_rows = m->psi_rows.as<double>();
+		sa.write_beta = write_beta;
+		sa.psi_partials = want_psi_partials ? m->vpartials.as<double>() : nullptr;
+		Launch l(m, KK_SCATTER_MSTEP);
+		launch_scatter(sa, m->docs, m->stream);
+	}
+	m->beta_valid = write_beta;
+	return check_launch(m, "mstep");
+}
+
+// copies n doubles device -> pinned host and waits
+int read_back(trlda_model* m, const double* dev, size_t n, double* out) {
+	CUDA_TRY(m, m->readback.ensure(sizeof(double) * n));
+	CUDA_TRY(m, cudaMemcpyAsync(m->readback.p, dev, sizeof(double) * n, cudaMemcpyDeviceToHost, m->stream));
+	CUDA_TRY(m, cudaStreamSynchronize(m->stream));
+	memcpy(out, m->readback.p, sizeof(double) * n);
+	m->stats.d2h_bytes += sizeof(double) * n;
+	return TRLDA_OK;
+}
+
+// psiGammaDiff_k = sum_d [psi(gamma_dk) - psi(sum_k gamma_dk)] over the whole (global) minibatch
+int alpha_statistics(trlda_model* m, std::vector<double>& diff) {
+	// doc_stat is free after the M-step: reuse it for the per-document terms
+	{
+		Launch l(m, KK_ALPHA_STATS);
+		launch_alpha_stats(m->gamma.as<double>(), m->K, m->docs.B, m->doc_stat.as<double>(), m->stream);
+	}
+	const int P = colsum_num_partials(m->docs.B);
+	CUDA_TRY(m, m->partials.ensure(sizeof(double) * (size_t) std::max(P, rowsum_num_partials(m->V)) * m->K));
+	{
+		Launch l(m, KK_REDUCE);
+		launch_colsum(m->doc_stat.as<double>(), m->K, m->docs.B, m->partials.as<double>(), m->rows_stat.as<double>(), m->stream);
+	}
+	TRY(check_launch(m, "alpha_stats"));
+	TRY(allreduce(m, m->rows_stat.p, m->K, ncclDouble));
+	diff.resize(m->K);
+	return read_back(m, m->rows_stat.as<double>(), m->K, diff.data());
+}
+
+// Newton direction pieces (onlinelda.cpp:128-134, batchlda.cpp:90-96, cumulativelda.cpp:98-104)
+double alpha_newton(const std::vector<double>& alpha, const std::vector<double>& diff, double n,
+                    std::vector<double>& g, std::vector<double>& h) {
+	const int K = (int) alpha.size();
+	double asum = 0.0;
+	for(int k = 0; k < K; ++k)
+		asum += alpha[k];
+	const double psi_asum = digamma(asum);
+	double sgh = 0.0, sih = 0.0;
+	g.resize(K);
+	h.resize(K);
+	for(int k = 0; k < K; ++k) {
+		g[k] = diff[k] - n * (digamma(alpha[k]) - psi_asum);
+		h[k] = -n * host_polygamma(1, alpha[k]);
+		sgh += g[k] / h[k];
+		sih += 1. / h[k];
+	}
+	const double z = n * host_polygamma(1, asum);
+	return sgh / (1. / z + sih);
+}
+
+double alpha_objective(const std::vector<double>& a, const std::vector<double>& diff, double n) {
+	double lg = 0.0, lin = 0.0, sum = 0.0;
+	for(size_t k = 0; k < a.size(); ++k) {
+		lg += lgamma(a[k]);
+		lin += diff[k] * (a[k] - 1.);
+		sum += a[k];
+	}
+	return n * (lgamma(sum) - lg) + lin;     // batchlda.cpp:82-83
+}
+
+// line-searched Newton ascent on alpha (batchlda.cpp:82-142, cumulativelda.cpp:91-150)
+void alpha_line_search(trlda_model* m, const std::vector<double>& diff, double n, const trlda_params* p) {
+	const int K = m->K;
+	std::vector<double> g, h, a(K);
+	double L = alpha_objective(m->alpha, diff, n);
+	double Lprime = L;
+	for(int i = 0; i < p->max_iter_alpha; ++i) {
+		if(p->verbosity > 1)
+			printf("\tCurrent function value: %g\n", L);
+		const double c = alpha_newton(m->alpha, diff, n, g, h);
+		double rho = .2;
+		for(int j = 0; j < 20; ++j) {
+			bool small = false;
+			for(int k = 0; k < K; ++k) {
+				a[k] = m->alpha[k] - rho * (g[k] - c) / h[k];
+				if(a[k] < p->min_alpha)
+					small = true;
+			}
+			if(small) {
+				rho /= 2.;
+				continue;
+			}
+			Lprime = alpha_objective(a, diff, n);
+			if(L <= Lprime) {
+				m->alpha = a;
+				break;
+			}
+			rho /= 2.;
+		}
+		if(Lprime - L < p->emp_bayes_threshold)
+			break;
+		L = Lprime;
+	}
+}
+
+// sum psi(lambda) - V sum_k psi(sum_w lambda_kw) from the per-word partials and psi_rows (onlinelda.cpp:153)
+int eta_constant(trlda_model* m, double* out) {
+	{
+		Launch l(m, KK_REDUCE);
+		launch_sum(m->vpartials.as<double>(), m->V, m->scalars.as<double>() + 16, m->scalars.as<double>(), m->stream);
+	}
+	{
+		Launch l(m, KK_REDUCE);
+		launch_sum(m->psi_rows.as<double>(), m->K, m->scalars.as<double>() + 16 + 1024, m->scalars.as<double>() + 1, m->stream);
+	}
+	TRY(check_launch(m, "eta_sums"));
+	double h[2];
+	TRY(read_back(m, m->scalars.as<double>(), 2, h));
+	*out = h[0] - m->V * h[1];
+	return TRLDA_OK;
+}
+
+int begin_update(trlda_model* m) {
+	TRY(set_device(m));
+	TRY(ensure_beta(m));
+	TRY(ensure_small(m));
+	CUDA_TRY(m, m->lam[1 - m->cur].ensure(kv_bytes(m)));
+	return TRLDA_OK;
+}
+
+void consume_injections(trlda_model* m) {
+	m->inj_gamma_cols = -1;
+	m->inj_gamma.clear();
+	m->inj_gamma.shrink_to_fit();
+	m->inj_lambda.clear();
+	m->inj_lambda.shrink_to_fit();
+}
+
+// ---- OnlineLDA::updateParameters, onlinelda.cpp:53-180 ---------------------------------------------------------------
+int online_update(trlda_model* m, const trlda_params* p, double* result) {
+	const int64_t B = m->global_B;
+	if(B == 0) {
+		*result = 1.0;                                               // :54-56 (returns `true`), counter untouched
+		return TRLDA_OK;
+	}
+	TRY(begin_update(m));
+
+	double rho = p->rho;                                             // :59-66
+	if(rho < 0.) {
+		if(p->adaptive)
+			rho = m->ada_rho;
+		else
+			rho = pow(p->tau + (double) m->update_count, -p->kappa);
+	}
+	const double scale = (double) m->num_documents / (double) B;
+	MStepCoef coef{MSTEP_ONLINE, rho, m->eta, scale};
+	const double eta_at_mstep = m->eta;
+	bool have_psi_partials = false;
+	bool have_dense_sstats = false;
+
+	if(p->update_lambda) {
+		const double* prime = m->lambda();                           // lambdaPrime = mLambda, :68 (no copy: buffer swap)
+		double* target = m->lambda_next();
+		TRY(compute_rows(m, prime, m->rows_prev.as<double>()));
+
+		if(p->max_iter_tr > 0) {
+			// phi = 1/K warm start, :79-86
+			CUDA_TRY(m, m->wordcount.ensure(sizeof(double) * m->V));
+			{
+				Launch l(m, KK_MISC);
+				launch_wordcount(m->docs, m->V, m->wordcount.as<double>(), m->stream);
+			}
+			TRY(allreduce(m, m->wordcount.p, m->V, ncclDouble));
+			const double scale_k = (double) m->num_documents / (double) B / (double) m->K;
+			{
+				Launch l(m, KK_MISC);
+				launch_rows_update(m->rows_prev.as<double>(), nullptr, 1. - rho,
+				                   rho * (m->V * m->eta + scale_k * (double) m->docs_total_count), 0., m->K,
+				                   m->rows.as<double>(), m->psi_rows.as<double>(), m->stream);
+			}
+			{
+				Launch l(m, KK_INIT_UPDATE);
+				launch_init_update(m->docs, m->K, m->V, rho, m->eta, scale_k, prime, target, m->psi_rows.as<double>(),
+				                   m->beta.p, m->beta_elem, m->wordcount.as<double>(), m->stream);
+			}
+			TRY(check_launch(m, "init_update"));
+			m->beta_valid = true;
+
+			for(int i = 0; i < p->max_iter_tr; ++i) {                 // :89-101
+				const bool last = i == p->max_iter_tr - 1;
+				TRY(run_estep(m, (i > 0 && p->init_gamma) ? GAMMA_KEEP : GAMMA_FRESH, nullptr, p->max_iter_inference, p->threshold));
+				const bool dense = last && p->adaptive;
+				TRY(run_mstep(m, coef, prime, target, !last, last && p->update_eta, dense));
+				have_psi_partials = last && p->update_eta;
+				have_dense_sstats = dense || m->nranks > 1;
+			}
+		} else {                                                     // :102-110
+			TRY(prepare_beta(m));
+			TRY(run_estep(m, GAMMA_FRESH, nullptr, p->max_iter_inference, p->threshold));
+			TRY(run_mstep(m, coef, prime, target, false, p->update_eta, p->adaptive));
+			have_psi_partials = p->update_eta;
+			have_dense_sstats = p->adaptive || m->nranks > 1;
+		}
+		m->cur = 1 - m->cur;                                         // the new lambda becomes current
+	}
+
+	if(p->update_alpha) {                                            // :116-142
+		if(!p->update_lambda) {
+			TRY(prepare_beta(m));
+			TRY(run_estep(m, GAMMA_FRESH, nullptr, p->max_iter_inference, p->threshold));
+		}
+		std::vector<double> diff, g, h;
+		TRY(alpha_statistics(m, diff));
+		const double c = alpha_newton(m->alpha, diff, (double) B, g, h);
+		for(int k = 0; k < m->K; ++k) {
+			m->alpha[k] = m->alpha[k] - rho * (g[k] - c) / h[k];
+			if(m->alpha[k] < p->min_alpha)
+				m->alpha[k] = p->min_alpha;
+		}
+		TRY(upload_alpha(m));
+	}
+
+	if(p->update_eta) {                                              // :147-162
+		if(!have_psi_partials)
+			TRY(prepare_beta(m, true));
+		double c = 0.0;
+		TRY(eta_constant(m, &c));
+		const int K = m->K, N = m->V;
+		const double g = c - (double) K * N * (digamma(m->eta) - digamma(N * m->eta));
+		const double h = (double) K * N * (host_polygamma(1, N * m->eta) - host_polygamma(1, m->eta));
+		m->eta = m->eta - rho * g / h;
+		if(m->eta < p->min_eta)
+			m->eta = p->min_eta;
+	}
+
+	if(p->update_lambda && p->adaptive) {                            // :167-175
+		if(!have_dense_sstats)
+			return fail(m, TRLDA_ERR_CUDA, "internal error: dense sufficient statistics missing for the adaptive rate");
+		const size_t KV = (size_t) m->K * m->V;
+		if(!m->ada_gradient.p) {
+			CUDA_TRY(m, m->ada_gradient.ensure(kv_bytes(m)));
+			CUDA_TRY(m, cudaMemsetAsync(m->ada_gradient.p, 0, kv_bytes(m), m->stream));
+		}
+		const int nb = adaptive_num_blocks((int64_t) KV);
+		// after the swap the old lambda (= lambda') sits in the non-current buffer
+		{
+			Launch l(m, KK_MISC);
+			launch_adaptive(m->sstats.as<double>(), m->lambda_next(), m->ada_gradient.as<double>(), (int64_t) KV, eta_at_mstep,
+			                scale, m->ada_tau, m->scalars.as<double>(), m->stream);
+		}
+		TRY(check_launch(m, "adaptive"));
+		std::vector<double> part(2 * nb);
+		TRY(read_back(m, m->scalars.as<double>(), 2 * nb, part.data()));
+		double sq = 0.0, gsq = 0.0;
+		for(int i = 0; i < nb; ++i) {
+			sq += part[i];
+			gsq += part[nb + i];
+		}
+		m->ada_sq_norm = (1. - 1. / m->ada_tau) * m->ada_sq_norm + 1. / m->ada_tau * sq;
+		m->ada_rho = gsq / m->ada_sq_norm;
+		m->ada_tau = m->ada_tau * (1. - m->ada_rho) + 1.;
+	}
+
+	m->update_count++;                                               // :177
+	*result = rho;
+	return TRLDA_OK;
+}
+
+
+
+// ---- BatchLDA::updateParameters, batchlda.cpp:43-209 -------------------------------------------------------------------
+int batch_update(trlda_model* m, const trlda_params* p, double* result) {
+	const int64_t B = m->global_B;
+	*result = 1.;
+	if(B == 0)
+		return TRLDA_OK;
+	TRY(begin_update(m));
+
+	for(int epoch = 0; epoch < p->max_epochs; ++epoch) {
+		bool have_psi_partials = false;
+		if(p->update_lambda) {                                       // :54-61
+			TRY(prepare_beta(m));
+			TRY(run_estep(m, GAMMA_FRESH, nullptr, p->max_iter_inference, p->threshold));
+			MStepCoef coef{MSTEP_BATCH, 1., m->eta, 1.};
+			TRY(run_mstep(m, coef, nullptr, m->lambda_next(), true, p->update_eta, false));
+			m->cur = 1 - m->cur;
+			have_psi_partials = p->update_eta;
+		}
+
+		if(p->update_alpha) {                                        // :66-143
+			if(!p->update_lambda) {
+				TRY(prepare_beta(m));
+				TRY(run_estep(m, GAMMA_FRESH, nullptr, p->max_iter_inference, p->threshold));
+			}
+			std::vector<double> diff;
+			TRY(alpha_statistics(m, diff));
+			if(p->verbosity > 1)
+				printf("Optimizing alpha...\n");
+			alpha_line_search(m, diff, (double) B, p);
+			TRY(upload_alpha(m));
+		}
+
+		if(p->update_eta) {                                          // :147-205
+			if(!have_psi_partials)
+				TRY(prepare_beta(m, true));
+			double c = 0.0;
+			TRY(eta_constant(m, &c));
+			const double K = m->K, N = m->V;
+			if(p->verbosity > 1)
+				printf("Optimizing eta...\n");
+			double L = (m->eta - 1) * c + K * lgamma(N * m->eta) - K * N * lgamma(m->eta);
+			double Lprime = L;
+			for(int i = 0; i < p->max_iter_eta; ++i) {
+				if(p->verbosity > 1)
+					printf("\tCurrent function value: %g\n", L);
+				const double g = c - K * N * (digamma(m->eta) - digamma(N * m->eta));
+				const double h = K * N * (host_polygamma(1, N * m->eta) - host_polygamma(1, m->eta));
+				double rho = .5;
+				for(int j = 0; j < 20; ++j) {
+					const double eta = m->eta - rho * g / h;
+					if(eta < p->min_eta) {
+						rho /= 2.;
+						continue;
+					}
+					Lprime = (eta - 1) * c + K * lgamma(N * eta) - K * N * lgamma(eta);
+					if(L <= Lprime) {
+						m->eta = eta;
+						break;
+					}
+					rho /= 2.;
+				}
+				if(Lprime - L < p->emp_bayes_threshold)
+					break;
+				L = Lprime;
+			}
+		}
+	}
+	return TRLDA_OK;
+}
+
+// ---- CumulativeLDA::updateParameters, cumulativelda.cpp:49-153 ----------------------------------------------------------
+int cumulative_update(trlda_model* m, const trlda_params* p, double* result) {
+	const int64_t B = m->global_B;
+	*result = 1.;
+	if(B == 0)
+		return TRLDA_OK;
+	TRY(begin_update(m));
+
+	// lambdaPrime = mLambda (:57); mLambda = random (:60) — even when update_lambda is false
+	const int prime_buf = m->cur;
+	const double* prime = m->lam[prime_buf].as<double>();
+	double* work = m->lam[1 - prime_buf].as<double>();
+	if(!m->inj_lambda.empty()) {
+		CUDA_TRY(m, cudaMemcpyAsync(work, m->inj_lambda.data(), kv_bytes(m), cudaMemcpyHostToDevice, m->stream));
+		CUDA_TRY(m, cudaStreamSynchronize(m->stream));
+		m->stats.h2d_bytes += kv_bytes(m);
+	} else {
+		Launch l(m, KK_RNG);
+		launch_gamma_rng(work, (int64_t) m->K * m->V, current_seed(), next_stream_id(), m->stream);
+	}
+	m->cur = 1 - prime_buf;
+	m->beta_valid = false;
+
+	if(p->update_lambda && p->max_epochs > 0) {                      // :62-71
+		TRY(compute_rows(m, prime, m->rows_prev.as<double>()));
+		// lambda = lambda' + sstats is rebuilt in place over the random lambda: each word's column is read
+		// (through beta) and rewritten by the same CTA
+		for(int epoch = 0; epoch < p->max_epochs; ++epoch) {
+			TRY(prepare_beta(m));
+			TRY(run_estep(m, GAMMA_FRESH, nullptr, p->max_iter_inference, p->threshold));
+			MStepCoef coef{MSTEP_CUMULATIVE, 1., m->eta, 1.};
+			TRY(run_mstep(m, coef, prime, work, true, false, false));
+		}
+	}
+
+	if(p->update_alpha) {                                            // :76-150
+		TRY(prepare_beta(m));
+		TRY(run_estep(m, GAMMA_FRESH, nullptr, p->max_iter_inference, p->threshold));
+		std::vector<double> diff;
+		TRY(alpha_statistics(m, diff));
+		if(m->psi_gamma_diff.size() != (size_t) m->K)
+			m->psi_gamma_diff.assign(m->K, 0.0);
+		for(int k = 0; k < m->K; ++k)
+			m->psi_gamma_diff[k] += diff[k];                         // :84
+		m->cum_num_documents += B;                                   // :85
+		if(p->verbosity > 1)
+			printf("Optimizing alpha...\n");
+		alpha_line_search(m, m->psi_gamma_diff, (double) m->cum_num_documents, p);
+		TRY(upload_alpha(m));
+	}
+	return TRLDA_OK;
+}
+
+int update_resident(trlda_model* m, const trlda_params* p, double* result) {
+	if(p->inference_method != TRLDA_INFERENCE_VI)
+		return fail(m, TRLDA_ERR_UNSUPPORTED, "Only variational inference ('VI') is implemented on the device.");
+	double r = 1.0;
+	int status;
+	switch(m->kind) {
+		case TRLDA_KIND_ONLINE: status = online_update(m, p, &r); break;
+		case TRLDA_KIND_BATCH: status = batch_update(m, p, &r); break;
+		default: status = cumulative_update(m, p, &r); break;
+	}
+	consume_injections(m);
+	if(status != TRLDA_OK)
+		return status;
+	CUDA_TRY(m, cudaStreamSynchronize(m->stream));
+	if(result)
+		*result = r;
+	return TRLDA_OK;
+}
+
+void collect_spans(trlda_model* m) {
+	for(auto& s : m->spans) {
+		float ms = 0.f;
+		if(cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess)
+			m->stats.ms[s.kind] += ms;
+		m->event_pool.push_back(s.a);
+		m->event_pool.push_back(s.b);
+	}
+	m->spans.clear();
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+void trlda_params_default(trlda_params* p) {
+	p->inference_method = TRLDA_INFERENCE_VI;
+	p->threshold = 0.001;
+	p->max_iter_inference = 100;
+	p->max_iter_tr = 10;
+	p->tau = 100.;
+	p->kappa = .7;
+	p->rho = -1.;
+	p->adaptive = 0;
+	p->num_samples = 1;
+	p->burn_in = 2;
+	p->init_gamma = 1;
+	p->update_lambda = 1;
+	p->update_alpha = 0;
+	p->update_eta = 0;
+	p->min_alpha = 1e-6;
+	p->min_eta = 1e-6;
+	p->max_epochs = 100;
+	p->max_iter_alpha = 10;
+	p->max_iter_eta = 20;
+	p->emp_bayes_threshold = 1e-8;
+	p->verbosity = 0;
+}
+
+const char* trlda_kernel_kind_name(int kind) {
+	static const char* names[TRLDA_NUM_KERNEL_KINDS] = {
+		"rowsum", "beta_prep", "estep", "scatter_mstep", "scatter", "mstep", "init_update", "reduce",
+		"alpha_stats", "rng", "elbo", "misc"};
+	return kind >= 0 && kind < TRLDA_NUM_KERNEL_KINDS ? names[kind] : "?";
+}
+
+const char* trlda_last_error(const trlda_model* m) { return m ? m->error.c_str() : g_error.c_str(); }
+
+void trlda_seed(uint64_t seed) {
+	std::lock_guard<std::mutex> lock(g_seed_mutex);
+	g_seed = seed;
+	g_stream_counter = 0;
+}
+
+int trlda_create(int kind, int num_words, int num_topics, int64_t num_documents, const double* alpha, double eta,
+                 int device, int precision, trlda_model** out) {
+	if(!out)
+		return fail(nullptr, TRLDA_ERR_ARG, "Null output pointer.");
+	*out = nullptr;
+	if(kind < TRLDA_KIND_ONLINE || kind > TRLDA_KIND_CUMULATIVE)
+		return fail(nullptr, TRLDA_ERR_ARG, "Unknown model kind.");
+	if(num_words <= 0 || num_topics <= 0)
+		return fail(nullptr, TRLDA_ERR_ARG, "The number of words and topics must be positive.");
+	if(num_topics > 4096)
+		return fail(nullptr, TRLDA_ERR_UNSUPPORTED, "More than 4096 topics are not supported.");
+	if(num_documents < 0)
+		return fail(nullptr, TRLDA_ERR_ARG, "The number of documents should not be negative.");
+	if(!alpha)
+		return fail(nullptr, TRLDA_ERR_ARG, "Alpha has wrong dimensionality.");
+	for(int k = 0; k < num_topics; ++k)
+		if(alpha[k] < 0.)
+			return fail(nullptr, TRLDA_ERR_ARG, "Alpha should not be negative.");
+	if(precision != TRLDA_PRECISION_FP64 && precision != TRLDA_PRECISION_MIXED)
+		return fail(nullptr, TRLDA_ERR_ARG, "Unknown precision mode.");
+
+	int count = 0;
+	if(cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+		return fail(nullptr, TRLDA_ERR_CUDA, "No CUDA device available; trlda_b200 has no CPU fallback.");
+	if(device < 0 || device >= count)
+		return fail(nullptr, TRLDA_ERR_CUDA, "CUDA device ordinal out of range.");
+
+	trlda_model* m = new trlda_model();
+	m->kind = kind;
+	m->K = num_topics;
+	m->V = num_words;
+	m->num_documents = num_documents;
+	m->eta = eta;
+	m->alpha.assign(alpha, alpha + num_topics);
+	m->device = device;
+	m->precision = precision;
+	m->psi_gamma_diff.assign(num_topics, 0.0);
+	if(const char* fc = getenv("TRLDA_ESTEP_CLUSTER"))
+		m->force_cluster = atoi(fc);
+
+	auto cleanup = [&](int code) {
+		std::string msg = m->error;
+		trlda_destroy(m);
+		g_error = msg;
+		return code;
+	};
+	cudaDeviceProp prop;
+	if(cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+		fail(m, TRLDA_ERR_CUDA, "Cannot select the CUDA device.");
+		return cleanup(TRLDA_ERR_CUDA);
+	}
+	if(prop.major < 10) {
+		fail(m, TRLDA_ERR_CUDA, "trlda_b200 kernels are built for sm_100a (B200) only.");
+		return cleanup(TRLDA_ERR_CUDA);
+	}
+	m->smem_optin = (int) prop.sharedMemPerBlockOptin;
+	m->num_sms = prop.multiProcessorCount;
+	if(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess) {
+		fail(m, TRLDA_ERR_CUDA, "Cannot create a CUDA stream.");
+		return cleanup(TRLDA_ERR_CUDA);
+	}
+	configure_estep(m->smem_optin);
+
+	int status = TRLDA_OK;
+	auto init = [&]() -> int {
+		CUDA_TRY(m, m->lam[0].ensure(kv_bytes(m)));
+		TRY(ensure_small(m));
+		TRY(upload_alpha(m));
+		if(kind == TRLDA_KIND_CUMULATIVE) {
+			launch_fill(m->lambda(), (int64_t) m->K * m->V, eta, m->stream);             // cumulativelda.cpp:30
+		} else {
+			launch_gamma_rng(m->lambda(), (int64_t) m->K * m->V, current_seed(), next_stream_id(), m->stream);   // lda.cpp:71
+		}
+		TRY(check_launch(m, "lambda init"));
+		CUDA_TRY(m, cudaStreamSynchronize(m->stream));
+		return TRLDA_OK;
+	};
+	status = init();
+	if(status != TRLDA_OK)
+		return cleanup(status);
+	*out = m;
+	return TRLDA_OK;
+}
+
+void trlda_destroy(trlda_model* m) {
+	if(!m)
+		return;
+	cudaSetDevice(m->device);
+	if(m->stream)
+		cudaStreamSynchronize(m->stream);
+	if(m->comm && nccl_api().ok)
+		nccl_api().CommDestroy(m->comm);
+	collect_spans(m);
+	for(cudaEvent_t e : m->event_pool)
+		cudaEventDestroy(e);
+	DevBuf* bufs[] = {&m->ada_gradient, &m->lam[0], &m->lam[1], &m->beta, &m->sstats, &m->rows, &m->rows_prev, &m->rows_stat,
+	                  &m->psi_rows, &m->d_alpha, &m->partials, &m->vpartials, &m->scalars, &m->b_doc_ptr, &m->b_word_ids,
+	                  &m->b_counts, &m->b_word_ptr, &m->b_tok_doc, &m->b_tok_src, &m->wordcount, &m->gamma, &m->etheta,
+	                  &m->etheta32, &m->weight, &m->doc_stat, &m->iterations};
+	for(DevBuf* b : bufs)
+		b->release();
+	m->staging.release();
+	m->readback.release();
+	if(m->stream)
+		cudaStreamDestroy(m->stream);
+	delete m;
+}
+
+int trlda_kind(const trlda_model* m) { return m->kind; }
+int trlda_precision(const trlda_model* m) { return m->precision; }
+
+int trlda_set_precision(trlda_model* m, int precision) {
+	if(precision != TRLDA_PRECISION_FP64 && precision != TRLDA_PRECISION_MIXED)
+		return fail(m, TRLDA_ERR_ARG, "Unknown precision mode.");
+	if(precision != m->precision) {
+		m->precision = precision;
+		m->beta_valid = false;
+		m->beta.release();
+	}
+	return TRLDA_OK;
+}
+
+int trlda_num_topics(const trlda_model* m) { return m->K; }
+int trlda_num_words(const trlda_model* m) { return m->V; }
+
+int trlda_get_lambda(trlda_model* m, double* out) {
+	TRY(set_device(m));
+	CUDA_TRY(m, cudaMemcpyAsync(out, m->lambda(), kv_bytes(m), cudaMemcpyDeviceToHost, m->stream));
+	CUDA_TRY(m, cudaStreamSynchronize(m->stream));
+	m->stats.d2h_bytes += kv_bytes(m);
+	return TRLDA_OK;
+}
+
+int trlda_set_lambda(trlda_model* m, const double* lambda, int rows, int cols) {
+	if(rows != m->K || cols != m->V || !lambda)
+		return fail(m, TRLDA_ERR_ARG, "Lambda has wrong dimensionality.");      // lda.h:187
+	TRY(set_device(m));
+	CUDA_TRY(m, cudaMemcpyAsync(m->lambda(), lambda, kv_bytes(m), cudaMemcpyHostToDevice, m->stream));
+	CUDA_TRY(m, cudaStreamSynchronize(m->stream));
+	m->stats.h2d_bytes += kv_bytes(m);
+	m->beta_valid = false;
+	return TRLDA_OK;
+}
+
+int trlda_get_alpha(trlda_model* m, double* out) {
+	memcpy(out, m->alpha.data(), sizeof(double) * m->K);
+	return TRLDA_OK;
+}
+
+int trlda_set_alpha(trlda_model* m, const double* alpha, int n) {
+	if(n == 1 && m->K != 1) {                                                  // setAlpha(double), lda.h:146-150
+		if(alpha[0] < 0.)
+			return fail(m, TRLDA_ERR_ARG, "Alpha should not be negative.");
+		std::fill(m->alpha.begin(), m->alpha.end(), alpha[0]);
+	} else {                                                                   // setAlpha(ArrayXd), lda.h:154-160
+		if(n != m->K)
+			return fail(m, TRLDA_ERR_ARG, "Alpha has wrong dimensionality.");
+		for(int k = 0; k < n; ++k)
+			if(alpha[k] < 0.)
+				return fail(m, TRLDA_ERR_ARG, "Alpha should not be negative.");
+		m->alpha.assign(alpha, alpha + n);
+	}
+	TRY(set_device(m));
+	return upload_alpha(m);
+}
+
+int trlda_get_eta(trlda_model* m, double* eta) {
+	*eta = m->eta;
+	return TRLDA_OK;
+}
+
+int trlda_set_eta(trlda_model* m, double eta) {
+	if(eta < 0.)
+		return fail(m, TRLDA_ERR_ARG, "Eta should not be negative.");          // lda.h:173
+	m->eta = eta;
+	return TRLDA_OK;
+}
+
+int trlda_get_num_documents(trlda_model* m, int64_t* n) {
+	*n = m->num_documents;
+	return TRLDA_OK;
+}
+
+int trlda_set_num_documents(trlda_model* m, int64_t n) {
+	if(n < 0)
+		return fail(m, TRLDA_ERR_ARG, "The number of documents should not be negative.");   // onlinelda.h:58
+	m->num_documents = n;
+	return TRLDA_OK;
+}
+
+int trlda_get_update_count(trlda_model* m, int64_t* n) {
+	*n = m->update_count;
+	return TRLDA_OK;
+}
+
+int trlda_set_update_count(trlda_model* m, int64_t n) {
+	if(n < 0)
+		return fail(m, TRLDA_ERR_ARG, "The update count should not be negative.");          // onlinelda.h:72
+	m->update_count = n;
+	return TRLDA_OK;
+}
+
+int trlda_upload_docs(trlda_model* m, const trlda_docs* docs) { return upload_docs(m, docs); }
+
+int trlda_update_variables(trlda_model* m, const trlda_docs* docs, const double* latents, int latents_rows,
+                           int64_t latents_cols, const trlda_params* params, double* gamma_out, double* sstats_out) {
+	if(params->inference_method != TRLDA_INFERENCE_VI)
+		return fail(m, TRLDA_ERR_UNSUPPORTED, "Only variational inference ('VI') is implemented on the device.");
+	if(latents && (latents_rows != m->K || latents_cols != docs->num_docs))
+		return fail(m, TRLDA_ERR_ARG, "Initial gamma has wrong dimensionality.");   // lda.cpp:166
+	TRY(upload_docs(m, docs));
+	TRY(prepare_beta(m));
+	TRY(run_estep(m, latents ? GAMMA_HOST : GAMMA_FRESH, latents, params->max_iter_inference, params->threshold));
+	if(sstats_out)
+		TRY(run_scatter_dense(m));
+	if(gamma_out && m->docs.B) {
+		CUDA_TRY(m, cudaMemcpyAsync(gamma_out, m->gamma.p, sizeof(double) * (size_t) m->K * m->docs.B, cudaMemcpyDeviceToHost, m->stream));
+		m->stats.d2h_bytes += sizeof(double) * (size_t) m->K * m->docs.B;
+	}
+	if(sstats_out) {
+		CUDA_TRY(m, cudaMemcpyAsync(sstats_out, m->sstats.p, kv_bytes(m), cudaMemcpyDeviceToHost, m->stream));
+		m->stats.d2h_bytes += kv_bytes(m);
+	}
+	CUDA_TRY(m, cudaStreamSynchronize(m->stream));
+	// iteration statistics of this E-step
+	if(m->docs.B) {
+		std::vector<int32_t> it(m->docs.B);
+		CUDA_TRY(m, cudaMemcpy(it.data(), m->iterations.p, sizeof(int32_t) * m->docs.B, cudaMemcpyDeviceToHost));
+		int64_t total = 0;
+		for(int32_t v : it)
+			total += v;
+		m->stats.estep_doc_iterations = total;
+	}
+	consume_injections(m);
+	return TRLDA_OK;
+}
+
+int trlda_update_parameters(trlda_model* m, const trlda_docs* docs, const trlda_params* params, double* result) {
+	TRY(upload_docs(m, docs));
+	return update_resident(m, params, result);
+}
+
+int trlda_update_parameters_resident(trlda_model* m, const trlda_params* params, double* result) {
+	if(!m->docs_resident)
+		return fail(m, TRLDA_ERR_ARG, "No minibatch resident on the device; call trlda_upload_docs first.");
+	TRY(set_device(m));
+	return update_resident(m, params, result);
+}
+
+int trlda_lower_bound(trlda_model* m, const trlda_docs* docs, const double* latents, int latents_rows,
+                      int64_t latents_cols, const trlda_params* params, int64_t num_documents, double* bound_out,
+                      double* per_doc_out) {
+	if(params->inference_method != TRLDA_INFERENCE_VI)
+		return fail(m, TRLDA_ERR_UNSUPPORTED, "Only variational inference ('VI') is implemented on the device.");
+	if(latents && (latents_rows != m->K || latents_cols != docs->num_docs))
+		return fail(m, TRLDA_ERR_ARG, "Initial gamma has wrong dimensionality.");
+	TRY(upload_docs(m, docs));
+	const int64_t B = m->docs.B;
+	if(m->kind == TRLDA_KIND_ONLINE && num_documents < 0)
+		num_documents = m->num_documents;                                      // onlinelda.cpp:184-191
+	const double factor = num_documents >= 0 ? (double) num_documents / (double) m->global_B : 1.;   // lda.cpp:303-304
+	TRY(prepare_beta(m));                                                      // also leaves rows / psi_rows of lambda
+	TRY(run_estep(m, latents ? GAMMA_HOST : GAMMA_FRESH, latents, params->max_iter_inference, params->threshold));   // :307
+
+	double lg_alpha = 0.0, asum = 0.0;
+	for(int k = 0; k < m->K; ++k) {
+		lg_alpha += lgamma(m->alpha[k]);
+		asum += m->alpha[k];
+	}
+	const double alpha_const = lgamma(asum) - lg_alpha;                         // :355
+	// per-document terms -> weight buffer is free after the E-step? keep it; use doc_stat for B values
+	double* per_doc = m->doc_stat.as<double>();
+	{
+		Launch l(m, KK_ELBO);
+		launch_elbo_docs(m->docs, m->K, m->lambda(), m->psi_rows.as<double>(), m->d_alpha.as<double>(), alpha_const,
+		                 m->gamma.as<double>(), per_doc, m->stream);
+	}
+	{
+		Launch l(m, KK_ELBO);
+		launch_elbo_beta(m->lambda(), m->psi_rows.as<double>(), m->K, m->V, m->eta, m->vpartials.as<double>(), m->stream);
+	}
+	double* sc = m->scalars.as<double>();
+	{
+		Launch l(m, KK_REDUCE);
+		launch_sum(per_doc, B, sc + 16, sc, m->stream);
+		launch_sum(m->vpartials.as<double>(), m->V, sc + 16 + 1024, sc + 1, m->stream);
+		launch_lgamma_vector(m->rows.as<double>(), m->K, m->rows_stat.as<double>(), m->stream);
+		launch_sum(m->rows_stat.as<double>(), m->K, sc + 16 + 2048, sc + 2, m->stream);
+	}
+	TRY(check_launch(m, "elbo"));
+	TRY(allreduce(m, sc, 1, ncclDouble));                                      // documents are sharded; beta terms are replicated
+	double h[3];
+	TRY(read_back(m, sc, 3, h));
+	double beta_terms = h[1];
+	beta_terms -= (double) m->K * m->V * lgamma(m->eta);                        // :357
+	beta_terms += m->K * lgamma(m->V * m->eta) - h[2];                          // :356
+	if(bound_out)
+		*bound_out = beta_terms + factor * h[0];
+	if(per_doc_out && B) {
+		CUDA_TRY(m, cudaMemcpy(per_doc_out, per_doc, sizeof(double) * B, cudaMemcpyDeviceToHost));
+		m->stats.d2h_bytes += sizeof(double) * B;
+	}
+	consume_injections(m);
+	return TRLDA_OK;
+}
+
+int trlda_inject_initial_gamma(trlda_model* m, const double* gamma0, int rows, int64_t cols) {
+	if(!gamma0 || rows != m->K || cols < 0)
+		return fail(m, TRLDA_ERR_ARG, "Initial gamma has wrong dimensionality.");
+	m->inj_gamma.assign(gamma0, gamma0 + (size_t) rows * cols);
+	m->inj_gamma_cols = cols;
+	return TRLDA_OK;
+}
+
+int trlda_inject_initial_lambda(trlda_model* m, const double* lambda, int rows, int cols) {
+	if(!lambda || rows != m->K || cols != m->V)
+		return fail(m, TRLDA_ERR_ARG, "Lambda has wrong dimensionality.");
+	m->inj_lambda.assign(lambda, lambda + (size_t) rows * cols);
+	return TRLDA_OK;
+}
+
+int trlda_comm_unique_id(void* id_out) {
+	if(!nccl_api().ok)
+		return fail(nullptr, TRLDA_ERR_CUDA, "libnccl.so.2 could not be loaded.");
+	static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
+	ncclUniqueId id;
+	ncclResult_t r = nccl_api().GetUniqueId(&id);
+	if(r != ncclSuccess)
+		return fail(nullptr, TRLDA_ERR_CUDA, std::string("NCCL error: ") + nccl_api().GetErrorString(r));
+	memcpy(id_out, &id, sizeof(id));
+	return TRLDA_OK;
+}
+
+int trlda_comm_init(trlda_model* m, const void* id_bytes, int rank, int nranks) {
+	if(nranks < 1 || rank < 0 || rank >= nranks)
+		return fail(m, TRLDA_ERR_ARG, "Invalid rank / world size.");
+	if(nranks == 1)
+		return TRLDA_OK;
+	if(!nccl_api().ok)
+		return fail(m, TRLDA_ERR_CUDA, "libnccl.so.2 could not be loaded.");
+	TRY(set_device(m));
+	ncclUniqueId id;
+	memcpy(&id, id_bytes, sizeof(id));
+	NCCL_TRY(m, nccl_api().CommInitRank(&m->comm, nranks, id, rank));
+	m->rank = rank;
+	m->nranks = nranks;
+	return TRLDA_OK;
+}
+
+int trlda_comm_size(const trlda_model* m) { return m->nranks; }
+
+void* trlda_stream(trlda_model* m) { return m->stream; }
+
+int trlda_synchronize(trlda_model* m) {
+	TRY(set_device(m));
+	CUDA_TRY(m, cudaStreamSynchronize(m->stream));
+	return TRLDA_OK;
+}
+
+int trlda_set_profiling(trlda_model* m, int on) {
+	m->profiling = on != 0;
+	return TRLDA_OK;
+}
+
+int trlda_get_stats(trlda_model* m, trlda_stats* out) {
+	TRY(set_device(m));
+	CUDA_TRY(m, cudaStreamSynchronize(m->stream));
+	collect_spans(m);
+	// inner-iteration total of the most recent E-step
+	if(m->gamma_valid && m->docs.B) {
+		std::vector<int32_t> it(m->docs.B);
+		CUDA_TRY(m, cudaMemcpy(it.data(), m->iterations.p, sizeof(int32_t) * m->docs.B, cudaMemcpyDeviceToHost));
+		int64_t total = 0;
+		for(int32_t v : it)
+			total += v;
+		m->stats.estep_doc_iterations = total;
+		m->stats.estep_docs = m->docs.B;
+	}
+	*out = m->stats;
+	return TRLDA_OK;
+}
+
+int trlda_reset_stats(trlda_model* m) {
+	TRY(set_device(m));
+	CUDA_TRY(m, cudaStreamSynchronize(m->stream));
+	collect_spans(m);
+	m->stats = trlda_stats{};
+	return TRLDA_OK;
+}
+
+int trlda_get_row_sums(trlda_model* m, double* out) {
+	TRY(set_device(m));
+	TRY(ensure_small(m));
+	TRY(compute_rows(m, m->lambda(), m->rows_stat.as<double>()));
+	return read_back(m, m->rows_stat.as<double>(), m->K, out);
+}
+
+int trlda_device_special(int device, int which, const double* x, int64_t n, double* out) {
+	if(cudaSetDevice(device) != cudaSuccess)
+		return fail(nullptr, TRLDA_ERR_CUDA, "No CUDA device available; trlda_b200 has no CPU fallback.");
+	double *dx = nullptr, *dy = nullptr;
+	if(cudaMalloc(&dx, sizeof(double) * n) != cudaSuccess || cudaMalloc(&dy, sizeof(double) * n) != cudaSuccess) {
+		cudaFree(dx);
+		return fail(nullptr, TRLDA_ERR_CUDA, "cudaMalloc failed.");
+	}
+	cudaMemcpy(dx, x, sizeof(double) * n, cudaMemcpyHostToDevice);
+	launch_special(which, dx, n, dy, 0);
+	cudaError_t e = cudaMemcpy(out, dy, sizeof(double) * n, cudaMemcpyDeviceToHost);
+	cudaFree(dx);
+	cudaFree(dy);
+	if(e != cudaSuccess)
+		return fail(nullptr, TRLDA_ERR_CUDA, std::string("CUDA error: ") + cudaGetErrorString(e));
+	return TRLDA_OK;
+}
+
+double trlda_polygamma(int n, double x) { return host_polygamma(n, x); }
+
+}  // extern "C"

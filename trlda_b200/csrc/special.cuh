@@ -1,0 +1,127 @@
+// special.cuh — in-register special functions for the sm_100a kernels.
+//
+// The reference evaluates psi with the scalar Cephes routine (code/trlda/src/digamma.cpp:116-178): upward
+// recurrence w = sum 1/(x+i) until s >= 10, then log(s) - 1/(2s) - sum_k B_2k/(2k s^2k) with the seven
+// coefficients of digamma.cpp:42-52, and psi' as the Hurwitz zeta(2, x) (zeta.cpp:67-134 via utils.cpp:107).
+// The device versions keep the same mathematical decomposition (same shift point, same series) so that the
+// results agree to a few ulp, but are restructured for a GPU: the recurrence is accumulated as a rational
+// num/den (two FMAs per step, ONE division in total) instead of one division per step.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math.h>
+
+namespace trlda {
+
+// B_2k / (2k), k = 7..1 in Horner order (same constants as digamma.cpp:42-52)
+__host__ __device__ __forceinline__ double psi_series(double z) {
+	double p = 8.33333333333333333333E-2;
+	p = fma(p, z, -2.10927960927960927961E-2);
+	p = fma(p, z, 7.57575757575757575758E-3);
+	p = fma(p, z, -4.16666666666666666667E-3);
+	p = fma(p, z, 3.96825396825396825397E-3);
+	p = fma(p, z, -8.33333333333333333333E-3);
+	p = fma(p, z, 8.33333333333333333333E-2);
+	return z * p;
+}
+
+// psi(x) for x > 0.
+__host__ __device__ __forceinline__ double digamma_pos(double x) {
+	double num = 0.0, den = 1.0, s = x;
+	// sum_{i<n} 1/(x+i) = num/den; at most 10 steps (all terms positive: no cancellation)
+	#pragma unroll 1
+	while(s < 10.0) {
+		num = fma(num, s, den);
+		den *= s;
+		s += 1.0;
+	}
+	const double r = 1.0 / s;
+	const double y = psi_series(r * r);
+	return log(s) - 0.5 * r - y - num / den;
+}
+
+// psi(x) for any x, following the reflection branch of digamma.cpp:123-144 for x <= 0 (never taken on the
+// hot path, where all arguments are positive).
+__host__ __device__ inline double digamma_reflect(double x) {
+	const double kPi = 3.141592653589793238462643383279502884;
+	double p = floor(x);
+	if(p == x)
+		return HUGE_VAL;
+	double nz = x - p;
+	if(nz != 0.5) {
+		if(nz > 0.5) {
+			p += 1.0;
+			nz = x - p;
+		}
+		nz = kPi / tan(kPi * nz);
+	} else {
+		nz = 0.0;
+	}
+	return digamma_pos(1.0 - x) - nz;
+}
+
+__host__ __device__ __forceinline__ double digamma(double x) {
+	if(x <= 0.0)
+		return digamma_reflect(x);
+	return digamma_pos(x);
+}
+
+// exp(psi(x)), the quantity the E-step actually needs (lda.cpp:174,197), x > 0.
+__device__ __forceinline__ double exp_digamma(double x) {
+	return exp(digamma(x));
+}
+
+// psi'(x) = zeta(2, x) for x > 0: shift to s >= 10 by the recurrence psi'(x) = psi'(x+1) + 1/x^2, then the
+// asymptotic series 1/s + 1/(2 s^2) + sum B_2k / s^(2k+1).  Only K+1 values per alpha update are needed
+// (onlinelda.cpp:132-133), so clarity beats speed here.
+__host__ __device__ __forceinline__ double trigamma(double x) {
+	double w = 0.0, s = x;
+	while(s < 10.0) {
+		w += 1.0 / (s * s);
+		s += 1.0;
+	}
+	const double r = 1.0 / s, z = r * r;
+	// B2 = 1/6, B4 = -1/30, B6 = 1/42, B8 = -1/30, B10 = 5/66, B12 = -691/2730, B14 = 7/6
+	double p = 7.0 / 6.0;
+	p = fma(p, z, -691.0 / 2730.0);
+	p = fma(p, z, 5.0 / 66.0);
+	p = fma(p, z, -1.0 / 30.0);
+	p = fma(p, z, 1.0 / 42.0);
+	p = fma(p, z, -1.0 / 30.0);
+	p = fma(p, z, 1.0 / 6.0);
+	return w + r + 0.5 * z + p * z * r;
+}
+
+// ---- float32 variants for the mixed-precision E-step ---------------------------------------------------------
+
+// exp(psi(x)) evaluated in float32 arithmetic for x > 0.  Same decomposition; the series is truncated to
+// the three terms float32 can resolve at s >= 6, and the shift point is lowered to 6 accordingly.
+__device__ __forceinline__ float exp_digamma_f32(float x) {
+	float num = 0.0f, den = 1.0f, s = x;
+	#pragma unroll 1
+	while(s < 6.0f) {
+		num = fmaf(num, s, den);
+		den *= s;
+		s += 1.0f;
+	}
+	const float r = __frcp_rn(s);
+	const float z = r * r;
+	float p = -3.96825396825e-3f;               // -B6/6
+	p = fmaf(p, z, 8.33333333333e-3f);          //  -B4/4 -> sign folded below
+	p = fmaf(p, z, -8.33333333333e-2f);         // -B2/2
+	// psi = log(s) - r/2 + z*p - num/den
+	const float psi = logf(s) - 0.5f * r + z * p - __fdividef(num, den);
+	return expf(psi);
+}
+
+// ---- warp / block reductions ---------------------------------------------------------------------------------
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+	#pragma unroll
+	for(int o = 16; o > 0; o >>= 1)
+		v += __shfl_xor_sync(0xffffffffu, v, o);
+	return v;
+}
+
+}  // namespace trlda
