@@ -1,0 +1,286 @@
+"""
+GPU parity tests (`-m gpu`): the CUDA path, driven through the C ABI (include/trlda_b200.h) with host buffers,
+against the CPU oracle on the same seeded inputs and against the golden fixtures generated from the compiled
+reference.  Tolerances are BASELINE.json's: fp64 mode <= 1e-9 relative on gamma / lambda / alpha / eta; mixed
+(fp32 tile + fp32 inner products, fp64 accumulation) <= 1e-4 relative and per-document ELBO <= 1e-5 relative.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from common import (TOL_ELBO_MIXED, TOL_FP64, TOL_MIXED, load_case, random_docs, rel_err, rel_err_columns,
+	rel_err_elementwise, run_batch_case, run_cumulative_case, run_online_case)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def capi():
+	from trlda_b200 import capi
+	capi.lib()        # raises if libtrlda_b200.so is missing: the GPU tests never fall back to anything else
+	return capi
+
+
+def tol(precision):
+	return TOL_FP64 if precision == 'fp64' else TOL_MIXED
+
+
+# ---- special functions -----------------------------------------------------------------------------------------------
+def test_device_special_functions_vs_reference_fixture(capi):
+	case = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'special.npz'))
+	x = case['x']
+	for which, name, bound in ((0, 'digamma', 2e-14), (1, 'trigamma', 2e-14), (2, 'lngamma', 2e-13)):
+		got = capi.device_special(which, x)
+		scale = np.maximum(np.abs(case[name]), 1e-3)
+		assert np.max(np.abs(got - case[name]) / scale) < bound, name
+
+
+def test_device_digamma_known_answers(capi):
+	# python/tests/utils_test.py:35-41 (7 places)
+	x = np.array([.1, 1., 120., .01, .1, .4, 11.])
+	psi = capi.device_special(0, x[:3])
+	assert np.allclose(psi, [-10.423754940411, -0.5772156649015329, 4.7833192891185], rtol=0, atol=5e-8)
+	tri = capi.device_special(1, x[3:])
+	assert np.allclose(tri, [10001.6212135283, 101.433299150792758, 7.275356590529597, 0.09516633568168575], rtol=1e-10)
+
+
+# ---- E-step ----------------------------------------------------------------------------------------------------------
+ESTEP_SHAPES = [
+	# K, V, B, max_len, max_iter
+	(1, 10, 4, 6, 10),
+	(12, 60, 9, 30, 20),
+	(33, 45, 7, 40, 50),       # K not a multiple of 32
+	(100, 700, 40, 150, 20),   # cfg-1 topic count
+	(200, 500, 24, 120, 20),
+	(500, 400, 12, 150, 20),   # cfg-4 topic count: cluster of 2-4 CTAs per document
+	(1000, 600, 10, 150, 20),  # cfg-3 topic count: cluster of 8 CTAs per document
+	(1000, 600, 6, 150, 0),    # max_iter = 0: statistics from the initial gamma
+]
+
+
+@pytest.mark.parametrize('precision', ['fp64', 'mixed'])
+@pytest.mark.parametrize('K,V,B,max_len,max_iter', ESTEP_SHAPES)
+def test_update_variables_vs_oracle(capi, oracle_built, precision, K, V, B, max_len, max_iter):
+	rng = np.random.default_rng(K * 7 + B)
+	lists = random_docs(rng, B, V, min(V, max_len), empty=(1,) if B > 2 else (), duplicates=(2,) if B > 3 else ())
+	lam0 = np.asfortranarray(rng.gamma(100., .01, size=(V, K)).T)
+	g0 = np.asfortranarray(rng.gamma(100., .01, size=(B, K)).T)
+	alpha = rng.uniform(.05, .5, size=K)
+
+	port = oracle_built.PortModel('online', V, K, 1000, alpha, .2)
+	port.lambdas = lam0
+	want_gamma, want_sstats, want_it = port.update_variables(
+		oracle_built.CSR.from_lists(lists), g0, max_iter=max_iter, want_iterations=True)
+
+	model = capi.Model('online', V, K, 1000, alpha, .2, precision=precision)
+	model.lambdas = lam0
+	gamma, sstats = model.update_variables(capi.CSR.from_lists(lists), g0, max_iter=max_iter)
+	stats = model.stats()
+
+	assert rel_err_columns(gamma, want_gamma) < tol(precision)
+	assert rel_err(sstats, want_sstats) < tol(precision)
+	# sum of the statistics is the token mass of the minibatch regardless of phi
+	assert np.sum(sstats) == pytest.approx(sum(c for doc in lists for _, c in doc), rel=1e-6)
+	if precision == 'fp64':
+		assert stats['estep_doc_iterations'] == int(want_it.sum())    # identical early exits
+
+
+def test_update_variables_draws_gamma_when_no_latents(capi):
+	capi.seed(123)
+	rng = np.random.default_rng(0)
+	lists = random_docs(rng, 20, 50, 20)
+	model = capi.Model('online', 50, 16, 100, .1, .2)
+	gamma, sstats = model.update_variables(capi.CSR.from_lists(lists), max_iter=0)
+	# with max_iter = 0 gamma is the initial draw itself: Gamma(100, 1/100), mean 1, std .1 (lda.cpp:135)
+	assert gamma.shape == (16, 20) and np.all(gamma > 0)
+	assert abs(gamma.mean() - 1.) < .03 and abs(gamma.std() - .1) < .03
+	lam = model.lambdas                                               # lda.cpp:71, same law
+	assert abs(lam.mean() - 1.) < .02 and abs(lam.std() - .1) < .02
+
+
+def test_update_variables_long_documents_stream_from_l2(capi, oracle_built):
+	"""documents with more distinct words than fit in shared memory: the tail of the tile streams from L2"""
+	rng = np.random.default_rng(4)
+	K, V, B = 1000, 3000, 3
+	lists = [[(int(w), int(1 + rng.integers(5))) for w in rng.permutation(V)[:n]] for n in (2500, 17, 1200)]
+	lam0 = np.asfortranarray(rng.gamma(100., .01, size=(V, K)).T)
+	g0 = np.asfortranarray(rng.gamma(100., .01, size=(B, K)).T)
+	port = oracle_built.PortModel('online', V, K, 1000, .1, .2)
+	port.lambdas = lam0
+	want_gamma, want_sstats = port.update_variables(oracle_built.CSR.from_lists(lists), g0, max_iter=8)
+	for precision in ('fp64', 'mixed'):
+		model = capi.Model('online', V, K, 1000, .1, .2, precision=precision)
+		model.lambdas = lam0
+		gamma, sstats = model.update_variables(capi.CSR.from_lists(lists), g0, max_iter=8)
+		assert rel_err_columns(gamma, want_gamma) < tol(precision)
+		assert rel_err(sstats, want_sstats) < tol(precision)
+
+
+def test_wrong_latents_shape_raises_reference_message(capi):
+	model = capi.Model('online', 20, 4, 10)
+	docs = capi.CSR.from_lists([[(1, 1)], [(2, 2)]])
+	with pytest.raises(RuntimeError, match='Initial gamma has wrong dimensionality.'):     # lda.cpp:166
+		model.update_variables(docs, np.ones((4, 3)))
+	with pytest.raises(RuntimeError, match='Word ID out of range.'):
+		model.update_variables(capi.CSR.from_lists([[(20, 1)]]), np.ones((4, 1)))
+
+
+# ---- golden fixtures from the compiled reference ---------------------------------------------------------------------
+@pytest.mark.parametrize('precision', ['fp64', 'mixed'])
+@pytest.mark.parametrize('name', ['online_tr.npz', 'online_sgd.npz', 'online_adaptive.npz'])
+def test_online_golden(capi, name, precision):
+	case = load_case(name)
+	model = capi.Model('online', case['V'], case['K'], case['D'], case['alpha0'], case['eta0'], precision=precision)
+	out = run_online_case(model, capi.CSR, case)
+	t = tol(precision)
+	assert rel_err_columns(out['estep_gamma'], case['estep_gamma']) < t
+	assert rel_err(out['estep_sstats'], case['estep_sstats']) < t
+	assert out['rho'] == pytest.approx(float(case['rho']), rel=1e-14)
+	assert rel_err_elementwise(out['lambda1'], case['lambda1']) < t
+	assert rel_err_elementwise(out['alpha1'], case['alpha1']) < t
+	assert out['eta1'] == pytest.approx(float(case['eta1']), rel=t)
+	assert out['update_count1'] == int(case['update_count1'])
+
+
+@pytest.mark.parametrize('precision', ['fp64', 'mixed'])
+def test_batch_golden(capi, precision):
+	case = load_case('batch.npz')
+	model = capi.Model('batch', case['V'], case['K'], 0, case['alpha0'], case['eta0'], precision=precision)
+	out = run_batch_case(model, capi.CSR, case)
+	t = tol(precision) * (1 if precision == 'fp64' else 10)      # three epochs of line searches compound in mixed mode
+	assert out['rho'] == 1.
+	assert rel_err_elementwise(out['lambda1'], case['lambda1']) < t
+	assert rel_err_elementwise(out['alpha1'], case['alpha1']) < t
+	assert out['eta1'] == pytest.approx(float(case['eta1']), rel=t)
+
+
+@pytest.mark.parametrize('precision', ['fp64', 'mixed'])
+def test_cumulative_golden(capi, precision):
+	case = load_case('cumulative.npz')
+	model = capi.Model('cumulative', case['V'], case['K'], 0, case['alpha0'], case['eta0'], precision=precision)
+	assert np.all(model.lambdas == case['eta0'])                  # cumulativelda.cpp:30
+	out = run_cumulative_case(model, capi.CSR, case)
+	t = tol(precision) * (1 if precision == 'fp64' else 10)
+	for call in range(2):
+		assert rel_err_elementwise(out['lambda1_%d' % call], case['lambda1_%d' % call]) < t
+		assert rel_err_elementwise(out['alpha1_%d' % call], case['alpha1_%d' % call]) < t
+
+
+# ---- update_parameters against the oracle at larger shapes -----------------------------------------------------------
+@pytest.mark.parametrize('precision', ['fp64', 'mixed'])
+@pytest.mark.parametrize('K,V,B', [(100, 7000, 200), (1000, 2000, 64)])
+def test_online_update_parameters_vs_oracle(capi, oracle_built, precision, K, V, B):
+	"""cfg-1 (README example) in full and cfg-3's topic count on a reduced vocabulary, T=10, I=20, with the
+	empirical-Bayes updates on"""
+	from trlda_b200.synth import gamma_matrix, make_corpus
+	ptr, ids, cts = make_corpus(B, V, K, .1, .2, seed=1001)
+	lam0, g0 = gamma_matrix(K, V, 2001), gamma_matrix(K, B, 3001)
+	kwargs = dict(max_iter_tr=10, max_iter_inference=20, kappa=.7, tau=100., update_alpha=1, update_eta=1)
+
+	port = oracle_built.PortModel('online', V, K, 1000000, .1, .2)
+	port.lambdas = lam0
+	want_rho, want_gamma = port.update_parameters(oracle_built.CSR(ptr, ids, cts), gamma0=g0, want_gamma=True, **kwargs)
+
+	model = capi.Model('online', V, K, 1000000, .1, .2, precision=precision)
+	model.lambdas = lam0
+	rho = model.update_parameters(capi.CSR(ptr, ids, cts), gamma0=g0, **kwargs)
+
+	t = tol(precision)
+	assert rho == pytest.approx(want_rho, rel=1e-14)
+	assert rel_err_elementwise(model.lambdas, port.lambdas) < t
+	assert rel_err_elementwise(model.alpha, port.alpha) < t
+	assert model.eta == pytest.approx(port.eta, rel=t)
+	assert model.update_count == port.update_count == 1
+
+
+def test_update_count_and_empty_batch_semantics(capi):
+	"""onlinelda_test.py:113-124: update_parameters([]) is a no-op returning 1.0 and does not count"""
+	rng = np.random.default_rng(1)
+	model = capi.Model('online', 100, 10, 1000)
+	before = model.lambdas
+	assert model.update_parameters(capi.CSR([0], [], [])) == 1.0
+	assert model.update_count == 0
+	assert np.array_equal(model.lambdas, before)
+	docs = capi.CSR.from_lists(random_docs(rng, 10, 100, 5))
+	rho0 = model.update_parameters(docs, max_iter_inference=20)
+	rho1 = model.update_parameters(docs, max_iter_inference=20)
+	assert model.update_count == 2
+	assert rho0 == pytest.approx((100. + 0) ** -.7) and rho1 == pytest.approx((100. + 1) ** -.7)   # onlinelda.cpp:65
+	assert np.all(np.isfinite(model.lambdas))
+
+
+def test_resident_path_equals_host_path(capi):
+	"""bench.py's device-only leg (docs already in HBM) computes exactly what the host-buffer call computes"""
+	from trlda_b200.synth import gamma_matrix, make_corpus
+	K, V, B = 64, 500, 50
+	docs = capi.CSR(*make_corpus(B, V, K, .1, .2, seed=3))
+	lam0, g0 = gamma_matrix(K, V, 4), gamma_matrix(K, B, 5)
+	out = []
+	for resident in (False, True):
+		model = capi.Model('online', V, K, 10000, .1, .2)
+		model.lambdas = lam0
+		if resident:
+			model.upload_docs(docs)
+			model.update_parameters_resident(gamma0=g0, max_iter_inference=20)
+		else:
+			model.update_parameters(docs, gamma0=g0, max_iter_inference=20)
+		out.append(model.lambdas)
+	assert np.array_equal(out[0], out[1])
+
+
+def test_runs_are_bitwise_deterministic(capi):
+	from trlda_b200.synth import gamma_matrix, make_corpus
+	K, V, B = 200, 800, 96
+	docs = capi.CSR(*make_corpus(B, V, K, .1, .2, seed=8))
+	lam0, g0 = gamma_matrix(K, V, 9), gamma_matrix(K, B, 10)
+	out = []
+	for _ in range(2):
+		model = capi.Model('online', V, K, 10000, .1, .2, precision='mixed')
+		model.lambdas = lam0
+		model.update_parameters(docs, gamma0=g0, max_iter_inference=20, max_iter_tr=3)
+		out.append(model.lambdas)
+	assert np.array_equal(out[0], out[1])
+
+
+# ---- lower bound -----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('precision', ['fp64', 'mixed'])
+def test_lower_bound_vs_oracle(capi, oracle_built, precision):
+	from trlda_b200.synth import gamma_matrix, make_corpus
+	K, V, B, D = 50, 900, 80, 5000
+	ptr, ids, cts = make_corpus(B, V, K, .1, .2, mean_length=60, seed=21)
+	lam0, g0 = gamma_matrix(K, V, 22), gamma_matrix(K, B, 23)
+	port = oracle_built.PortModel('online', V, K, D, .1, .2)
+	port.lambdas = lam0
+	want_total, want_docs = port.lower_bound(oracle_built.CSR(ptr, ids, cts), g0, max_iter=50)
+	model = capi.Model('online', V, K, D, .1, .2, precision=precision)
+	model.lambdas = lam0
+	total, per_doc = model.lower_bound(capi.CSR(ptr, ids, cts), g0, max_iter=50)
+	t = 1e-9 if precision == 'fp64' else TOL_ELBO_MIXED
+	assert np.max(np.abs(per_doc - want_docs) / np.abs(want_docs)) < t
+	assert total == pytest.approx(want_total, rel=t)
+
+
+# ---- accessors / errors ----------------------------------------------------------------------------------------------
+def test_accessors_and_error_messages(capi):
+	"""onlinelda_test.py:14-35 through the C ABI"""
+	W, D, K = 102, 1010, 11
+	model = capi.Model('online', W, K, D, .27, 3.1)
+	assert (model.K, model.V, model.num_documents, model.eta) == (K, W, D, 3.1)
+	assert np.all(model.alpha == .27)
+	with pytest.raises(RuntimeError, match='Alpha has wrong dimensionality.'):
+		model.alpha = np.random.rand(K + 1)
+	with pytest.raises(RuntimeError, match='Alpha should not be negative.'):
+		model.alpha = -np.ones(K)
+	with pytest.raises(RuntimeError, match='Eta should not be negative.'):
+		model.eta = -1.
+	with pytest.raises(RuntimeError, match='Lambda has wrong dimensionality.'):
+		model.lambdas = np.ones((K, W + 1))
+	alpha = np.random.rand(K, 1)
+	model.alpha = alpha
+	assert np.max(np.abs(model.alpha - alpha.ravel())) < 1e-20
+	lam = np.random.rand(K, W)
+	model.lambdas = lam
+	assert np.array_equal(model.lambdas, lam) and model.lambdas.flags.f_contiguous
+	model.alpha = 2.5                                                # scalar form, lda.h:146
+	assert np.all(model.alpha == 2.5)

@@ -242,7 +242,7 @@ EStepPlan plan_estep(int K, int n_max, int elem, int smem_optin, int force_clust
 
 template <typename T, bool CLUSTERED>
 __global__ void __launch_bounds__(ESTEP_THREADS)
-k_estep(EStepArgs a, DeviceDocs docs, int C, int kc, int n_cap, int n_fit) {
+k_estep(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, int64_t doc_offset, int C, int kc, int n_cap, int n_fit) {
 	extern __shared__ __align__(16) unsigned char smem[];
 	const EStepSmem L = estep_smem_layout(C, kc, n_cap, n_fit, (int) sizeof(T));
 	T* tile = reinterpret_cast<T*>(smem + L.tile);
@@ -259,7 +259,8 @@ k_estep(EStepArgs a, DeviceDocs docs, int C, int kc, int n_cap, int n_fit) {
 
 	cg::cluster_group cluster = cg::this_cluster();
 	const int rank = CLUSTERED ? (int) cluster.block_rank() : 0;
-	const int64_t d = blockIdx.x / C;
+	const int64_t slot = doc_offset + blockIdx.x / C;
+	const int64_t d = order ? order[slot] : slot;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	constexpr int NW = ESTEP_THREADS / 32;
 	const int K = a.K;
@@ -464,9 +465,10 @@ void configure_estep(int smem_optin) {
 }
 
 template <typename T, bool CLUSTERED>
-static void launch_estep_t(const EStepPlan& plan, const EStepArgs& args, const DeviceDocs& docs, cudaStream_t s) {
+static void launch_estep_t(const EStepPlan& plan, const EStepArgs& args, const DeviceDocs& docs, const int32_t* order,
+                           int64_t offset, int64_t count, cudaStream_t s) {
 	cudaLaunchConfig_t cfg = {};
-	cfg.gridDim = dim3((unsigned) (docs.B * plan.cluster));
+	cfg.gridDim = dim3((unsigned) (count * plan.cluster));
 	cfg.blockDim = dim3(ESTEP_THREADS);
 	cfg.dynamicSmemBytes = plan.smem;
 	cfg.stream = s;
@@ -477,18 +479,19 @@ static void launch_estep_t(const EStepPlan& plan, const EStepArgs& args, const D
 	attr[0].val.clusterDim.z = 1;
 	cfg.attrs = attr;
 	cfg.numAttrs = CLUSTERED ? 1 : 0;
-	cudaLaunchKernelEx(&cfg, k_estep<T, CLUSTERED>, args, docs, plan.cluster, plan.kc, plan.n_cap, plan.n_fit);
+	cudaLaunchKernelEx(&cfg, k_estep<T, CLUSTERED>, args, docs, order, offset, plan.cluster, plan.kc, plan.n_cap, plan.n_fit);
 }
 
-void launch_estep(const EStepPlan& plan, const EStepArgs& args, const DeviceDocs& docs, int elem_size, cudaStream_t s) {
-	if(docs.B == 0)
+void launch_estep(const EStepPlan& plan, const EStepArgs& args, const DeviceDocs& docs, const int32_t* order,
+                  int64_t offset, int64_t count, int elem_size, cudaStream_t s) {
+	if(count == 0)
 		return;
 	if(elem_size == 8) {
-		if(plan.cluster > 1) launch_estep_t<double, true>(plan, args, docs, s);
-		else launch_estep_t<double, false>(plan, args, docs, s);
+		if(plan.cluster > 1) launch_estep_t<double, true>(plan, args, docs, order, offset, count, s);
+		else launch_estep_t<double, false>(plan, args, docs, order, offset, count, s);
 	} else {
-		if(plan.cluster > 1) launch_estep_t<float, true>(plan, args, docs, s);
-		else launch_estep_t<float, false>(plan, args, docs, s);
+		if(plan.cluster > 1) launch_estep_t<float, true>(plan, args, docs, order, offset, count, s);
+		else launch_estep_t<float, false>(plan, args, docs, order, offset, count, s);
 	}
 }
 

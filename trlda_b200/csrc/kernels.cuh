@@ -53,6 +53,7 @@ struct EStepPlan {
 	int n_cap = 0;        // capacity of the per-column vectors in shared memory
 	int n_fit = 0;        // columns of the tile kept in shared memory (the rest stream from L2)
 	size_t smem = 0;      // dynamic shared memory per CTA
+	bool fast = false;    // whole tile resident + TMA gather + vectorised passes (estep_fast.cu)
 };
 
 // plans the E-step launch for (K, longest document, element size of the expElogbeta working copy)
@@ -70,6 +71,7 @@ struct EStepArgs {
 	int32_t* iterations = nullptr;  // B out
 	int max_iter = 0;
 	double threshold = 0;
+	unsigned long long* ticks = nullptr;   // optional phase timers (debug, TRLDA_ESTEP_TICKS=1): 16 sums of clock64 deltas
 };
 
 void launch_rowsum(const double* lambda, int K, int V, double* partials, int* num_partials, cudaStream_t s);
@@ -84,8 +86,17 @@ void launch_rows_update(const double* rows_prev, const double* rows_stat, double
 void launch_beta_prep(const double* lambda, const double* psi_rows, int K, int V, void* beta, int elem_size,
                       double* psi_partials /* V values or null */, cudaStream_t s);
 
-void launch_estep(const EStepPlan& plan, const EStepArgs& args, const DeviceDocs& docs, int elem_size, cudaStream_t s);
+// documents order[offset .. offset+count) (order == nullptr: identity) are processed by one launch
+void launch_estep(const EStepPlan& plan, const EStepArgs& args, const DeviceDocs& docs, const int32_t* order,
+                  int64_t offset, int64_t count, int elem_size, cudaStream_t s);
 void configure_estep(int smem_optin);
+
+// tuned kernel for documents whose tile fits in the cluster's shared memory (estep_fast.cu); plan.cluster == 0
+// means "not applicable" (use the generic kernel)
+EStepPlan plan_estep_fast(int K, int n_max, int elem_size, int smem_optin, int force_cluster);
+void launch_estep_fast(const EStepPlan& plan, const EStepArgs& args, const DeviceDocs& docs, const int32_t* order,
+                       int64_t offset, int64_t count, int elem_size, cudaStream_t s);
+void configure_estep_fast(int smem_optin);
 
 // segmented scatter.  If `fused`, lambda/beta are rebuilt in the same pass (single-GPU path); else the dense
 // K x V statistics are written to `sstats`.

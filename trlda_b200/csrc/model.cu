@@ -196,7 +196,13 @@ struct trlda_model {
 
 	// minibatch
 	DeviceDocs docs;
-	DevBuf b_doc_ptr, b_word_ids, b_counts, b_word_ptr, b_tok_doc, b_tok_src, wordcount;
+	DevBuf b_doc_ptr, b_word_ids, b_counts, b_word_ptr, b_tok_doc, b_tok_src, b_order, wordcount;
+	// documents sorted by length (descending) and cut into buckets; each bucket is one E-step launch whose
+	// shared-memory tile is sized for the bucket's longest document
+	struct Bucket { int64_t offset, count; int n_max; };
+	std::vector<Bucket> buckets;
+	bool force_generic = false;
+	DevBuf ticks;    // debug phase timers of the fast E-step kernel (TRLDA_ESTEP_TICKS=1)
 	PinnedBuf staging, readback;
 	int64_t docs_total_count = 0;    // sum of all counts in the (global) minibatch
 	int64_t global_B = 0;            // documents over all ranks
@@ -394,7 +400,8 @@ int upload_docs(trlda_model* m, const trlda_docs* docs) {
 	const size_t o_wptr = o_cts + sizeof(int32_t) * N;
 	const size_t o_tdoc = o_wptr + sizeof(int32_t) * ((size_t) V + 1);
 	const size_t o_tsrc = o_tdoc + sizeof(int32_t) * N;
-	const size_t total = o_tsrc + sizeof(int32_t) * N;
+	const size_t o_order = o_tsrc + sizeof(int32_t) * N;
+	const size_t total = o_order + sizeof(int32_t) * std::max<int64_t>(B, 1);
 	CUDA_TRY(m, m->staging.ensure(total));
 	char* base = m->staging.as<char>();
 	int64_t* s_ptr = reinterpret_cast<int64_t*>(base + o_ptr);
@@ -403,6 +410,7 @@ int upload_docs(trlda_model* m, const trlda_docs* docs) {
 	int32_t* s_wptr = reinterpret_cast<int32_t*>(base + o_wptr);
 	int32_t* s_tdoc = reinterpret_cast<int32_t*>(base + o_tdoc);
 	int32_t* s_tsrc = reinterpret_cast<int32_t*>(base + o_tsrc);
+	int32_t* s_order = reinterpret_cast<int32_t*>(base + o_order);
 
 	// make sure the previous use of the staging buffer has been consumed
 	CUDA_TRY(m, cudaStreamSynchronize(m->stream));
@@ -444,6 +452,37 @@ int upload_docs(trlda_model* m, const trlda_docs* docs) {
 			}
 	}
 
+	// length buckets for the E-step: counting sort by length, longest first
+	m->buckets.clear();
+	if(B) {
+		std::vector<int32_t> start(n_max + 2, 0);
+		for(int64_t d = 0; d < B; ++d)
+			start[n_max - (int) (s_ptr[d + 1] - s_ptr[d]) + 1]++;
+		for(int i = 0; i <= n_max; ++i)
+			start[i + 1] += start[i];
+		for(int64_t d = 0; d < B; ++d)
+			s_order[start[n_max - (int) (s_ptr[d + 1] - s_ptr[d])]++] = (int32_t) d;
+		auto cap_of = [](int n) {
+			int cap = 32;
+			while(cap < n)
+				cap += cap < 256 ? 32 : (cap < 512 ? 64 : cap / 4);
+			return cap;
+		};
+		auto len_of = [&](int64_t i) { const int32_t d = s_order[i]; return (int) (s_ptr[d + 1] - s_ptr[d]); };
+		const int64_t min_bucket = 128;
+		for(int64_t i = 0; i < B;) {
+			const int cap = cap_of(len_of(i));
+			int64_t j = i;
+			while(j < B && (cap_of(len_of(j)) == cap || j - i < min_bucket))
+				++j;
+			if(B - j < min_bucket)
+				j = B;
+			m->buckets.push_back({i, j - i, len_of(i)});
+			i = j;
+		}
+	}
+
+	CUDA_TRY(m, m->b_order.ensure(sizeof(int32_t) * std::max<int64_t>(B, 1)));
 	CUDA_TRY(m, m->b_doc_ptr.ensure(sizeof(int64_t) * (B + 1)));
 	CUDA_TRY(m, m->b_word_ids.ensure(sizeof(int32_t) * std::max<int64_t>(N, 1)));
 	CUDA_TRY(m, m->b_counts.ensure(sizeof(int32_t) * std::max<int64_t>(N, 1)));
@@ -458,6 +497,8 @@ int upload_docs(trlda_model* m, const trlda_docs* docs) {
 		CUDA_TRY(m, cudaMemcpyAsync(m->b_tok_src.p, s_tsrc, sizeof(int32_t) * N, cudaMemcpyHostToDevice, m->stream));
 	}
 	CUDA_TRY(m, cudaMemcpyAsync(m->b_word_ptr.p, s_wptr, sizeof(int32_t) * ((size_t) V + 1), cudaMemcpyHostToDevice, m->stream));
+	if(B)
+		CUDA_TRY(m, cudaMemcpyAsync(m->b_order.p, s_order, sizeof(int32_t) * B, cudaMemcpyHostToDevice, m->stream));
 	m->stats.h2d_bytes += total;
 
 	m->docs.B = B;
@@ -529,9 +570,6 @@ int run_estep(trlda_model* m, GammaSource src, const double* host_gamma, int max
 		                            cudaMemcpyHostToDevice, m->stream));
 		m->stats.h2d_bytes += sizeof(double) * (size_t) m->K * m->docs.B;
 	}
-	const EStepPlan plan = plan_estep(m->K, m->docs.n_max, m->beta_elem, m->smem_optin, m->force_cluster);
-	if(plan.n_cap < m->docs.n_max || plan.smem > (size_t) m->smem_optin)
-		return fail(m, TRLDA_ERR_UNSUPPORTED, "A document has too many distinct words for the E-step kernel.");
 	EStepArgs a;
 	a.K = m->K;
 	a.beta = m->beta.p;
@@ -544,9 +582,21 @@ int run_estep(trlda_model* m, GammaSource src, const double* host_gamma, int max
 	a.iterations = m->iterations.as<int32_t>();
 	a.max_iter = max_iter;
 	a.threshold = threshold;
-	{
+	a.ticks = m->ticks.as<unsigned long long>();
+	for(const auto& bucket : m->buckets) {
+		EStepPlan plan;
+		plan.cluster = 0;
+		if(!m->force_generic)
+			plan = plan_estep_fast(m->K, bucket.n_max, m->beta_elem, m->smem_optin, m->force_cluster);
 		Launch l(m, KK_ESTEP);
-		launch_estep(plan, a, m->docs, m->beta_elem, m->stream);
+		if(plan.cluster > 0) {
+			launch_estep_fast(plan, a, m->docs, m->b_order.as<int32_t>(), bucket.offset, bucket.count, m->beta_elem, m->stream);
+		} else {
+			plan = plan_estep(m->K, bucket.n_max, m->beta_elem, m->smem_optin, m->force_cluster);
+			if(plan.n_cap < bucket.n_max || plan.smem > (size_t) m->smem_optin)
+				return fail(m, TRLDA_ERR_UNSUPPORTED, "A document has too many distinct words for the E-step kernel.");
+			launch_estep(plan, a, m->docs, m->b_order.as<int32_t>(), bucket.offset, bucket.count, m->beta_elem, m->stream);
+		}
 	}
 	m->gamma_valid = true;
 	m->stats.estep_docs = m->docs.B;
@@ -1149,6 +1199,11 @@ int trlda_create(int kind, int num_words, int num_topics, int64_t num_documents,
 	m->psi_gamma_diff.assign(num_topics, 0.0);
 	if(const char* fc = getenv("TRLDA_ESTEP_CLUSTER"))
 		m->force_cluster = atoi(fc);
+	if(const char* fg = getenv("TRLDA_ESTEP_GENERIC"))
+		m->force_generic = atoi(fg) != 0;
+	if(const char* ft = getenv("TRLDA_ESTEP_TICKS"))
+		if(atoi(ft) != 0 && m->ticks.ensure(16 * sizeof(unsigned long long)) == cudaSuccess)
+			cudaMemset(m->ticks.p, 0, 16 * sizeof(unsigned long long));
 
 	auto cleanup = [&](int code) {
 		std::string msg = m->error;
@@ -1172,6 +1227,7 @@ int trlda_create(int kind, int num_words, int num_topics, int64_t num_documents,
 		return cleanup(TRLDA_ERR_CUDA);
 	}
 	configure_estep(m->smem_optin);
+	configure_estep_fast(m->smem_optin);
 
 	int status = TRLDA_OK;
 	auto init = [&]() -> int {
@@ -1200,6 +1256,16 @@ void trlda_destroy(trlda_model* m) {
 	cudaSetDevice(m->device);
 	if(m->stream)
 		cudaStreamSynchronize(m->stream);
+	if(m->ticks.p) {
+		unsigned long long t[16];
+		cudaMemcpy(t, m->ticks.p, sizeof(t), cudaMemcpyDeviceToHost);
+		static const char* names[10] = {"stage+gather issue+psi0", "gather wait", "initial pass2+push", "initial exchange+W",
+		                                "pass1", "gamma/psi/delta", "pass2+push", "exchange+W", "results+doc_stat", "-"};
+		fprintf(stderr, "[trlda] fast E-step phase timers: %llu documents, %llu inner iterations\n", t[15], t[14]);
+		for(int i = 0; i < 10; ++i)
+			fprintf(stderr, "[trlda]   %-26s %10.0f cycles/doc\n", names[i], t[15] ? (double) t[i] / (double) t[15] : 0.0);
+		m->ticks.release();
+	}
 	if(m->comm && nccl_api().ok)
 		nccl_api().CommDestroy(m->comm);
 	collect_spans(m);
@@ -1207,7 +1273,7 @@ void trlda_destroy(trlda_model* m) {
 		cudaEventDestroy(e);
 	DevBuf* bufs[] = {&m->ada_gradient, &m->lam[0], &m->lam[1], &m->beta, &m->sstats, &m->rows, &m->rows_prev, &m->rows_stat,
 	                  &m->psi_rows, &m->d_alpha, &m->partials, &m->vpartials, &m->scalars, &m->b_doc_ptr, &m->b_word_ids,
-	                  &m->b_counts, &m->b_word_ptr, &m->b_tok_doc, &m->b_tok_src, &m->wordcount, &m->gamma, &m->etheta,
+	                  &m->b_counts, &m->b_word_ptr, &m->b_tok_doc, &m->b_tok_src, &m->b_order, &m->wordcount, &m->gamma, &m->etheta,
 	                  &m->etheta32, &m->weight, &m->doc_stat, &m->iterations};
 	for(DevBuf* b : bufs)
 		b->release();
