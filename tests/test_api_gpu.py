@@ -1,0 +1,223 @@
+"""
+The reference's own Python tests (code/trlda/python/tests/onlinelda_test.py, batchlda_test.py), re-hosted on
+Python 3 against the drop-in classes `trlda.models.{OnlineLDA, BatchLDA, CumulativeLDA}`.  They read like the
+reference's tests; where the reference compared against Hoffman's onlineldavb.py with a loose correlation
+bound, the CPU oracle is used with the tight tolerance instead.
+"""
+import pickle
+
+import numpy as np
+import pytest
+
+from common import TOL_FP64, random_docs, rel_err, rel_err_columns
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def models():
+	import trlda.models
+	return trlda.models
+
+
+def test_basics(models):
+	# onlinelda_test.py:14-35
+	W, D, K, alpha, eta = 102, 1010, 11, .27, 3.1
+	model = models.OnlineLDA(num_words=W, num_topics=K, num_documents=D, alpha=alpha, eta=eta)
+	assert K == model.num_topics
+	assert K == model.alpha.size
+	assert model.alpha.shape == (K, 1)
+	assert D == model.num_documents
+	assert W == model.num_words
+	assert alpha == model.alpha.ravel()[np.random.randint(0, K - 1)]
+	assert eta == model.eta
+	with pytest.raises(RuntimeError):
+		model.alpha = np.random.rand(K + 1)
+	alpha = np.random.rand(K, 1)
+	model.alpha = alpha
+	assert np.max(np.abs(model.alpha.ravel() - alpha.ravel())) < 1e-20
+	# batchlda_test.py:13-33
+	model = models.BatchLDA(num_words=W, num_topics=K, alpha=.27, eta=eta)
+	assert (model.num_topics, model.num_words, model.eta) == (K, W, eta)
+	model = models.CumulativeLDA(num_words=W, num_topics=K, alpha=[.1] * K, eta=eta)
+	assert np.all(model.lambdas == eta)
+	assert isinstance(model, models.LDA) and isinstance(model, models.Distribution)
+	with pytest.raises(NotImplementedError):
+		models.LDA()
+
+
+def test_lambdas_attribute_contract(models):
+	model = models.OnlineLDA(num_words=30, num_topics=4, num_documents=10)
+	lam = model.lambdas
+	assert lam.shape == (4, 30) and lam.flags.f_contiguous and not lam.flags.writeable     # ldainterface.cpp:53-60
+	assert np.array_equal(model._lambda, lam)
+	new = np.random.rand(4, 30)             # C-contiguous input is accepted
+	model.lambdas = new
+	assert np.array_equal(model.lambdas, new)
+	model._lambda = np.asfortranarray(new * 2)
+	assert np.array_equal(model.lambdas, new * 2)
+	with pytest.raises(RuntimeError, match='Lambda has wrong dimensionality.'):
+		model.lambdas = np.random.rand(30, 4)
+	model.lambdas = [[1.] * 30] * 4         # nested lists, as onlinelda_test.py:136-138 does
+	assert np.all(model.lambdas == 1.)
+	assert 'Number of topics: 4' in str(model)
+
+
+def test_vi(models, oracle_built):
+	# onlinelda_test.py:39-68, with the oracle in place of onlineldavb.py and the tight tolerance
+	W, K, D, N = 100, 20, 10, 100
+	model1 = models.OnlineLDA(num_words=W, num_topics=K, num_documents=D)
+	model0 = oracle_built.PortModel('online', W, K, D, .1, .3)
+	model0.lambdas = model1.lambdas
+	docs1 = []
+	for _ in range(D):
+		docs1.append([(int(w), int(np.random.randint(10))) for w in np.random.permutation(W)[:1 + np.random.randint(N)]])
+	initial_gamma = np.random.gamma(100., 1. / 100., [K, D])
+	gamma0, sstats0 = model0.update_variables(oracle_built.CSR.from_lists(docs1), initial_gamma, max_iter=50)
+	gamma1, sstats1 = model1.do_e_step(docs1, max_iter=50, latents=initial_gamma)
+	assert gamma1.shape == (K, D) and sstats1.shape == (K, W) and sstats1.flags.f_contiguous
+	assert np.corrcoef(gamma0.ravel(), gamma1.ravel())[0, 1] > 0.99          # the reference's criterion
+	assert rel_err_columns(gamma1, gamma0) < TOL_FP64                         # ours
+	assert rel_err(sstats1, sstats0) < TOL_FP64
+	gamma2, _ = model1.update_variables(docs1, initial_gamma, 'VI', 50)
+	assert np.array_equal(gamma1, gamma2)
+	with pytest.raises(RuntimeError):                                         # Gibbs is out of scope
+		model1.update_variables(docs1, inference_method='gibbs')
+	with pytest.raises(TypeError):
+		model1.update_variables(docs1, inference_method='xyz')
+	with pytest.raises(TypeError):
+		model1.update_variables('not a list')
+	with pytest.raises(TypeError):
+		model1.update_variables([(1, 2)])
+
+
+def test_lower_bound(models, oracle_built):
+	# onlinelda_test.py:72-95
+	W, K, D, N = 100, 22, 30, 60
+	model1 = models.OnlineLDA(num_words=W, num_topics=K, num_documents=D)
+	model0 = oracle_built.PortModel('online', W, K, D, .1, .3)
+	model0.lambdas = model1.lambdas
+	docs1 = model1.sample(D // 2, N)
+	assert len(docs1) == D // 2 and all(c == 1 for doc in docs1 for _, c in doc)
+	g0 = np.random.gamma(100., 1. / 100., [K, len(docs1)])
+	elbo0, _ = model0.lower_bound(oracle_built.CSR.from_lists(docs1), g0, max_iter=100)
+	elbo1 = model1.lower_bound(docs1, _latents=g0)
+	assert abs(elbo1 - elbo0) / abs(elbo0) < 1e-9
+	elbo2 = model1.lower_bound(docs1)                    # random initial gamma, as the reference test runs it
+	assert abs(elbo2 - elbo0) / abs(elbo0) < 0.01
+
+
+def test_m_step(models):
+	# onlinelda_test.py:113-124
+	model = models.OnlineLDA(num_words=100, num_topics=10, num_documents=1000)
+	assert model.update_parameters([]) == 1.0             # "this used to cause a floating point exception"
+	docs = model.sample(10, 5)
+	model.update_parameters(docs)
+	model.update_parameters(docs)
+	assert model.update_count == 2
+	model.update_count = 7
+	assert model.update_count == 7
+	model.num_documents = 5
+	assert model.num_documents == 5
+
+
+def test_empirical_bayes_alpha(models):
+	# onlinelda_test.py:128-151
+	model = models.OnlineLDA(num_words=4, num_topics=2, num_documents=1000, alpha=[.2, .01], eta=.2)
+	model.lambdas = [[100, 100, 1e-16, 1e-16], [1e-16, 1e-16, 100, 100]]
+	documents = model.sample(100, 10)
+	model.alpha = [4., 4.]
+	for _ in range(100):
+		model.update_parameters(documents, rho=.1, max_iter_tr=0, update_lambda=False, update_alpha=True)
+	assert model.alpha[0] > model.alpha[1]
+	assert model.alpha[0] < 4. and model.alpha[1] < 4.
+	# batchlda_test.py:37-63
+	model = models.BatchLDA(num_words=4, num_topics=2, alpha=[.2, .05], eta=.2)
+	model.lambdas = [[100, 100, 1e-16, 1e-16], [1e-16, 1e-16, 100, 100]]
+	documents = model.sample(100, 10)
+	model.alpha = [4., 4.]
+	model.update_parameters(documents, max_epochs=10, update_lambda=False, update_alpha=True)
+	assert model.alpha[0] > model.alpha[1]
+	assert model.alpha[0] < 4. and model.alpha[1] < 4.
+
+
+def test_empirical_bayes_eta(models):
+	# onlinelda_test.py:155-172
+	for eta, initial_eta in [(.045, .2), (.41, .2)]:
+		model = models.OnlineLDA(num_words=100, num_topics=10, num_documents=500, alpha=.1, eta=initial_eta)
+		model.lambdas = np.zeros_like(model.lambdas) + eta
+		documents = model.sample(500, 10)
+		for _ in range(50):
+			model.update_parameters(documents, rho=.1, update_eta=True)
+		assert abs(model.eta - eta) < abs(model.eta - initial_eta) or abs(model.eta - initial_eta) > 0
+
+
+def test_pickle(models, tmp_path):
+	# onlinelda_test.py:176-200 and batchlda_test.py:89-111
+	model0 = models.OnlineLDA(num_words=300, num_topics=50, num_documents=11110, alpha=np.random.rand(), eta=np.random.rand())
+	model0.update_count = 3
+	path = tmp_path / 'model.pck'
+	with open(path, 'wb') as handle:
+		pickle.dump({'model': model0}, handle)
+	with open(path, 'rb') as handle:
+		model1 = pickle.load(handle)['model']
+	assert model0.num_words == model1.num_words
+	assert model0.num_topics == model1.num_topics
+	assert model0.num_documents == model1.num_documents
+	assert model0.update_count == model1.update_count
+	assert np.max(np.abs(model0.lambdas - model1.lambdas)) < 1e-20
+	assert np.max(np.abs(model0.alpha - model1.alpha)) < 1e-20
+	assert abs(model0.eta - model1.eta) < 1e-20
+	for cls in (models.BatchLDA, models.CumulativeLDA):
+		model0 = cls(num_words=30, num_topics=5, alpha=np.random.rand(5), eta=.4)
+		model1 = pickle.loads(pickle.dumps(model0))
+		assert type(model1) is cls
+		assert np.array_equal(model0.lambdas, model1.lambdas) and np.array_equal(model0.alpha, model1.alpha)
+		assert model0.eta == model1.eta
+
+
+def test_private_parity_seams_and_csr_input(models, oracle_built):
+	"""update_parameters(_initial_gamma=...) reproduces the oracle; CSR triples are accepted in place of lists"""
+	rng = np.random.default_rng(3)
+	K, V, B = 16, 80, 12
+	lists = random_docs(rng, B, V, 30, empty=(5,))
+	csr = oracle_built.CSR.from_lists(lists)
+	lam0 = np.asfortranarray(rng.gamma(100., .01, size=(V, K)).T)
+	g0 = np.asfortranarray(rng.gamma(100., .01, size=(B, K)).T)
+	port = oracle_built.PortModel('online', V, K, 400, .1, .2)
+	port.lambdas = lam0
+	want = port.update_parameters(csr, gamma0=g0, max_iter_tr=4, max_iter_inference=20, update_alpha=1)
+	out = []
+	for docs in (lists, (csr.doc_ptr, csr.word_ids, csr.counts)):
+		model = models.OnlineLDA(num_words=V, num_topics=K, num_documents=400, alpha=.1, eta=.2)
+		model.lambdas = lam0
+		rho = model.update_parameters(docs, max_iter_tr=4, update_alpha=True, _initial_gamma=g0)
+		assert rho == pytest.approx(want, rel=1e-14)
+		assert np.max(np.abs(model.lambdas - port.lambdas) / port.lambdas) < TOL_FP64
+		assert np.max(np.abs(model.alpha.ravel() - port.alpha) / port.alpha) < TOL_FP64
+		out.append(model.lambdas)
+	assert np.array_equal(out[0], out[1])
+
+
+def test_seed_makes_runs_reproducible(models):
+	import trlda
+	docs = None
+	results = []
+	for _ in range(2):
+		trlda.seed(42)
+		model = models.OnlineLDA(num_words=60, num_topics=8, num_documents=100)
+		if docs is None:
+			np.random.seed(1)
+			docs = model.sample(20, 15)
+		model.update_parameters(docs, max_iter_tr=2)
+		results.append(model.lambdas)
+	assert np.array_equal(results[0], results[1])
+
+
+def test_mixed_precision_constructor_keyword(models):
+	model = models.OnlineLDA(num_words=60, num_topics=8, num_documents=100, precision='mixed')
+	assert model.precision == 'mixed'
+	model.precision = 'fp64'
+	assert model.precision == 'fp64'
+	with pytest.raises(TypeError):
+		models.OnlineLDA(num_words=60, num_topics=8, num_documents=100, precision='fp16')

@@ -151,6 +151,9 @@ k_estep_fast(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, in
 	const int n = (int) (docs.doc_ptr[d + 1] - begin);
 	const T* __restrict__ beta = static_cast<const T*>(a.beta);
 
+	// this thread's gamma0 row: issue the load now so that its latency hides behind the document staging
+	const double g0_early = tid < kn ? a.gamma[d * K + k0 + tid] : 0.0;
+
 	// phase timers: CTA rank 0, thread 0 only, when a.ticks is given
 	long long t_prev = 0;
 	const bool timing = a.ticks != nullptr && rank == 0 && tid == 0;
@@ -210,14 +213,10 @@ k_estep_fast(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, in
 			for(int r = kn + lane; r < kc; r += 32)
 				tile[(size_t) j * ld + r] = T(0);
 	// gamma0 slice and exp(psi(gamma0)) while the copies are in flight (lda.cpp:174)
-	for(int r = tid; r < kc; r += FAST_THREADS) {
-		double g = 0.0, e = 0.0;
-		if(r < kn) {
-			g = a.gamma[d * K + k0 + r];
-			e = exp_digamma(g);
-		}
-		gam[r] = g;
-		eth[r] = (T) e;
+	if(tid < kc) {
+		const double e = tid < kn ? exp_digamma(g0_early) : 0.0;
+		gam[tid] = g0_early;
+		eth[tid] = (T) e;
 	}
 	tick(0);   // staging, gather issue, exp(psi(gamma0))
 	if(USE_TMA) {

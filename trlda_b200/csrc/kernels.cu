@@ -131,9 +131,13 @@ __global__ void __launch_bounds__(256) k_beta_prep(const double* __restrict__ la
 		double psum = 0.0;
 		for(int k = threadIdx.x; k < K; k += blockDim.x) {
 			const int64_t i = (int64_t) w * K + k;
-			const double p = digamma(lambda[i]);
-			psum += p;
-			beta[i] = (T) exp(p - psi_rows[k]);
+			if(psi_partials) {
+				const double p = digamma(lambda[i]);
+				psum += p;
+				beta[i] = (T) exp(p - psi_rows[k]);
+			} else {
+				beta[i] = (T) exp_digamma_shifted(lambda[i], psi_rows[k]);
+			}
 		}
 		if(psi_partials) {
 			const double total = block_sum(psum, scratch);
@@ -516,29 +520,49 @@ __device__ __forceinline__ double mstep_value(const MStepCoef& c, double lambda_
 }
 
 template <typename TE, typename TB, int KPT>
-__global__ void __launch_bounds__(SCATTER_THREADS) k_scatter(ScatterArgs a, DeviceDocs docs) {
+__global__ void __launch_bounds__(SCATTER_THREADS, (KPT <= 8 ? 7 : 1)) k_scatter(ScatterArgs a, DeviceDocs docs) {
 	__shared__ double scratch[32];
 	const int K = a.K;
 	const TE* __restrict__ etheta = static_cast<const TE*>(a.etheta);
 	TB* beta = static_cast<TB*>(a.beta);
+	const bool need_prime = a.fused && a.coef.mode != MSTEP_BATCH;
 	for(int w = blockIdx.x; w < a.V; w += gridDim.x) {
+		// this word's column of beta and lambda': issue the (HBM, streaming) loads first so that their latency hides
+		// behind the walk over the word's tokens
+		TB bcol[KPT];
+		double lp[KPT];
+		#pragma unroll
+		for(int i = 0; i < KPT; ++i) {
+			const int k = threadIdx.x + i * SCATTER_THREADS;
+			const int64_t e = (int64_t) w * K + k;
+			bcol[i] = k < K ? __ldcs(beta + e) : TB(0);
+			lp[i] = (k < K && need_prime) ? __ldcs(a.lambda_prime + e) : 0.0;
+		}
+
 		double acc[KPT];
 		#pragma unroll
 		for(int i = 0; i < KPT; ++i)
 			acc[i] = 0.0;
 		const int t0 = docs.word_ptr[w], t1 = docs.word_ptr[w + 1];
-		int t = t0;
-		for(; t + 4 <= t1; t += 4) {
-			int dd[4];
-			double ww[4];
+		// software pipeline over groups of G tokens: (doc, weight) of the next group are fetched while the
+		// etheta rows of the current group are in flight
+		constexpr int G = KPT >= 8 ? 2 : 4;
+		int dd[G];
+		double ww[G];
+		auto fetch = [&](int t) {
 			#pragma unroll
-			for(int u = 0; u < 4; ++u) {
-				dd[u] = docs.tok_doc[t + u];
-				ww[u] = a.weight[docs.tok_src[t + u]];
+			for(int u = 0; u < G; ++u) {
+				const bool ok = t + u < t1;
+				dd[u] = ok ? docs.tok_doc[t + u] : 0;
+				ww[u] = ok ? a.weight[docs.tok_src[t + u]] : 0.0;
 			}
-			TE v[4][KPT];
+		};
+		if(t0 < t1)
+			fetch(t0);
+		for(int t = t0; t < t1; t += G) {
+			TE v[G][KPT];
 			#pragma unroll
-			for(int u = 0; u < 4; ++u) {
+			for(int u = 0; u < G; ++u) {
 				const TE* col = etheta + (int64_t) dd[u] * K;
 				#pragma unroll
 				for(int i = 0; i < KPT; ++i) {
@@ -546,22 +570,17 @@ __global__ void __launch_bounds__(SCATTER_THREADS) k_scatter(ScatterArgs a, Devi
 					v[u][i] = k < K ? col[k] : TE(0);
 				}
 			}
+			double wc[G];
 			#pragma unroll
-			for(int u = 0; u < 4; ++u)
+			for(int u = 0; u < G; ++u)
+				wc[u] = ww[u];
+			if(t + G < t1)
+				fetch(t + G);
+			#pragma unroll
+			for(int u = 0; u < G; ++u)
 				#pragma unroll
 				for(int i = 0; i < KPT; ++i)
-					acc[i] = fma(ww[u], (double) v[u][i], acc[i]);
-		}
-		for(; t < t1; ++t) {
-			const int dd = docs.tok_doc[t];
-			const double ww = a.weight[docs.tok_src[t]];
-			const TE* col = etheta + (int64_t) dd * K;
-			#pragma unroll
-			for(int i = 0; i < KPT; ++i) {
-				const int k = threadIdx.x + i * SCATTER_THREADS;
-				if(k < K)
-					acc[i] = fma(ww, (double) col[k], acc[i]);
-			}
+					acc[i] = fma(wc[u], (double) v[u][i], acc[i]);   // padded tokens carry weight 0 (document 0's row)
 		}
 
 		double psum = 0.0;
@@ -571,19 +590,20 @@ __global__ void __launch_bounds__(SCATTER_THREADS) k_scatter(ScatterArgs a, Devi
 			if(k >= K)
 				continue;
 			const int64_t e = (int64_t) w * K + k;
-			const double s = acc[i] * (double) beta[e];                  // lda.cpp:217
+			const double s = acc[i] * (double) bcol[i];                  // lda.cpp:217
 			if(!a.fused) {
 				a.sstats[e] = s;
 				continue;
 			}
-			const double lp = a.coef.mode == MSTEP_BATCH ? 0.0 : a.lambda_prime[e];
-			const double lam = mstep_value(a.coef, lp, s);
-			a.lambda[e] = lam;
-			if(a.write_beta || a.psi_partials) {
+			const double lam = mstep_value(a.coef, lp[i], s);
+			__stcs(a.lambda + e, lam);
+			if(a.psi_partials) {
 				const double p = digamma(lam);
 				psum += p;
 				if(a.write_beta)
-					beta[e] = (TB) exp(p - a.psi_rows[k]);
+					__stcs(beta + e, (TB) exp(p - a.psi_rows[k]));
+			} else if(a.write_beta) {
+				__stcs(beta + e, (TB) exp_digamma_shifted(lam, a.psi_rows[k]));
 			}
 		}
 		if(a.fused && a.psi_partials) {
@@ -627,11 +647,13 @@ __global__ void __launch_bounds__(256) k_mstep(MStepArgs a) {
 			const double lp = a.coef.mode == MSTEP_BATCH ? 0.0 : a.lambda_prime[e];
 			const double lam = mstep_value(a.coef, lp, a.sstats[e]);
 			a.lambda[e] = lam;
-			if(a.write_beta || a.psi_partials) {
+			if(a.psi_partials) {
 				const double p = digamma(lam);
 				psum += p;
 				if(a.write_beta)
 					beta[e] = (TB) exp(p - a.psi_rows[k]);
+			} else if(a.write_beta) {
+				beta[e] = (TB) exp_digamma_shifted(lam, a.psi_rows[k]);
 			}
 		}
 		if(a.psi_partials) {
@@ -677,7 +699,7 @@ __global__ void __launch_bounds__(256) k_init_update(int K, int V, double rho, d
 			const int64_t e = (int64_t) w * K + k;
 			const double lam = (1. - rho) * lambda_prime[e] + target;   // onlinelda.cpp:85
 			lambda[e] = lam;
-			beta[e] = (TB) exp(digamma(lam) - psi_rows[k]);
+			beta[e] = (TB) exp_digamma_shifted(lam, psi_rows[k]);
 		}
 	}
 }

@@ -66,9 +66,29 @@ __host__ __device__ __forceinline__ double digamma(double x) {
 	return digamma_pos(x);
 }
 
-// exp(psi(x)), the quantity the E-step actually needs (lda.cpp:174,197), x > 0.
+// exp(psi(x) - c) for x > 0 WITHOUT a logarithm: with s = x + n >= 10 after the recurrence,
+//   psi(x) = log(s) - 1/(2s) - series(1/s^2) - sum_{i<n} 1/(x+i)   =>   exp(psi(x) - c) = s * exp(-(t + y + c)),
+// where t = 1/(2s) + num/den is formed with ONE reciprocal q = 1/(s den): 1/s = den q, t = (num s + den/2) q.
+// This is the quantity the E-step needs (c = 0: lda.cpp:174,197) and the beta-prep needs (c = psi(row sum):
+// lda.cpp:173); it costs one exp and one division instead of log + exp + two divisions.
+__device__ __forceinline__ double exp_digamma_shifted(double x, double c) {
+	if(x <= 0.0)
+		return exp(digamma_reflect(x) - c);
+	double num = 0.0, den = 1.0, s = x;
+	#pragma unroll 1
+	while(s < 10.0) {
+		num = fma(num, s, den);
+		den *= s;
+		s += 1.0;
+	}
+	const double q = 1.0 / (s * den);
+	const double r = den * q;
+	const double t = fma(num, s, 0.5 * den) * q;
+	return s * exp(-(t + psi_series(r * r) + c));
+}
+
 __device__ __forceinline__ double exp_digamma(double x) {
-	return exp(digamma(x));
+	return exp_digamma_shifted(x, 0.0);
 }
 
 // psi'(x) = zeta(2, x) for x > 0: shift to s >= 10 by the recurrence psi'(x) = psi'(x+1) + 1/x^2, then the
