@@ -135,46 +135,62 @@ def make_inputs(w, batch, rank, workload_name):
 # ----------------------------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the reference's CPU implementation on the host cores
 # ----------------------------------------------------------------------------------------------------------------------
+_CPU_MODEL = {}
+
+
 def cpu_model(w):
-	from oracle import pyoracle
-	if pyoracle.have_ref():
-		return pyoracle, pyoracle.RefModel('online', w['V'], w['K'], w['D'], w['alpha'], w['eta']), 'reference'
-	if not pyoracle.have_port():
-		pyoracle.build(ref=False)
-	return pyoracle, pyoracle.PortModel('online', w['V'], w['K'], w['D'], w['alpha'], w['eta']), 'port'
+	"""The CPU implementation, constructed once per process: the reference's constructor draws lambda with
+	100 K V calls to rand() (lda.cpp:71 -> utils.cpp:224-231), about two minutes at cfg-3, before we overwrite it."""
+	key = (w['V'], w['K'])
+	if key not in _CPU_MODEL:
+		from oracle import pyoracle
+		if pyoracle.have_ref():
+			_CPU_MODEL[key] = (pyoracle, pyoracle.RefModel('online', w['V'], w['K'], w['D'], w['alpha'], w['eta']), 'reference')
+		else:
+			if not pyoracle.have_port():
+				pyoracle.build(ref=False)
+			_CPU_MODEL[key] = (pyoracle, pyoracle.PortModel('online', w['V'], w['K'], w['D'], w['alpha'], w['eta']), 'port')
+	return _CPU_MODEL[key]
 
 
 def cpu_sample(w, docs, lam0, sizes, workload_name):
-	"""Times updateParameters(max_iter_tr=1, injected gamma0) of the CPU implementation at the given sample sizes
-	and extrapolates t(B) = a + b B to the full step: T (a + b B).  Returns (docs/s, seconds of CPU work, text)."""
+	"""Times updateParameters of the CPU implementation on a bounded sample and extrapolates to the full step.
+
+	Three calls with an injected gamma0: (B1, T=1), (B2, T=1), (B1, T=2).  With t(B, T) = c0 + T (a + b B) they give
+	the per-call cost c0 (rho, lambda' copy, phi=1/K warm start), the per-iteration fixed K x V cost a (psi / exp over
+	lambda, M-step expressions) and the per-document cost b; the full step is c0 + T (a + b B) at the workload's
+	B and T.  Returns (docs/s, seconds of the extrapolated step, seconds spent, kind, description)."""
 	from trlda_b200.synth import gamma_matrix
 	pyoracle, model, kind = cpu_model(w)
 	ptr, ids, cts = docs
 	params = dict(w['params'])
 	T = params['max_iter_tr']
-	params['max_iter_tr'] = 1
+	b1, b2 = sizes
+	runs = [(b1, 1), (b2, 1), (b1, 2)]
 	times = []
 	start_all = time.perf_counter()
-	for n in sizes:
+	for n, iters in runs:
 		csr = pyoracle.CSR(ptr[:n + 1], ids[:ptr[n]], cts[:ptr[n]])
 		g0 = gamma_matrix(w['K'], n, 3000 + CFG_INDEX[workload_name])
 		model.lambdas = lam0
+		model.update_count = 0
+		params['max_iter_tr'] = iters
 		t0 = time.perf_counter()
 		model.update_parameters(csr, gamma0=g0, **params)
 		times.append(time.perf_counter() - t0)
 	spent = time.perf_counter() - start_all
-	if len(sizes) >= 2 and sizes[-1] != sizes[0]:
-		b = max((times[-1] - times[0]) / (sizes[-1] - sizes[0]), 1e-9)
-		a = max(times[0] - b * sizes[0], 0.)
-	else:
-		a, b = 0., times[0] / sizes[0]
+	b = max((times[1] - times[0]) / (b2 - b1), 1e-9)
+	per_iter = max(times[2] - times[0], 1e-9)              # a + b * b1
+	a = max(per_iter - b * b1, 0.)
+	c0 = max(times[0] - per_iter, 0.)
 	B = w['B']
-	full = T * (a + b * B)
-	text = ('%s CPU core: updateParameters(max_iter_tr=1, injected gamma0) on the first %s documents of the workload '
-		'took %s s; linear model t=a+b*B (a=%.3f s fixed K*V cost, b=%.3f ms/doc) extrapolated to B=%d, T=%d '
-		'(RNG for gamma0 excluded, which favours the CPU)') % (
-		'unmodified reference (oracle/_ref)' if kind == 'reference' else 'plain-C port (oracle/lda_oracle.c)',
-		'/'.join(str(s) for s in sizes), '/'.join('%.2f' % t for t in times), a, b * 1e3, B, T)
+	full = c0 + T * (a + b * B)
+	text = ('%s on the host cores: updateParameters(injected gamma0) on the first documents of the workload, '
+		'(B, T) = %s took %s s; model t = c0 + T (a + b B) with c0=%.2f s per call, a=%.2f s per TR iteration '
+		'(fixed K*V cost), b=%.3f ms per document and iteration, extrapolated to B=%d, T=%d (the reference\'s rand() '
+		'draw of gamma0 is excluded, which favours the CPU)') % (
+		'unmodified reference core (oracle/_ref)' if kind == 'reference' else 'plain-C port (oracle/lda_oracle.c)',
+		', '.join('(%d, %d)' % r for r in runs), '/'.join('%.2f' % t for t in times), c0, a, b * 1e3, B, T)
 	return B / full, full, spent, kind, text
 
 
@@ -182,10 +198,10 @@ def reference_arm(args, w):
 	rank = int(os.environ.get('RANK', '0'))
 	if rank != 0:
 		return
-	docs, lam0 = make_inputs(w, 256, 0, args.workload)
+	docs, lam0 = make_inputs(w, 512, 0, args.workload)
 	cores = os.cpu_count() or 1
 	os.environ.setdefault('OMP_NUM_THREADS', str(cores))
-	sizes = [32, 96] if w['K'] >= 500 else [64, 200]
+	sizes = [64, 512]
 	# CPU code needs no warm-up beyond the first call; keep the whole run within a few minutes
 	total_steps = args.steps + args.warmup
 	values, fulls = [], []
@@ -255,11 +271,8 @@ def main():
 	model = capi.Model('online', V, K, w['D'], w['alpha'], w['eta'], device=local_rank, precision=args.precision)
 	model.lambdas = lam0
 	if world > 1:
-		uid = torch.zeros(128, dtype=torch.uint8, device='cuda')
-		if rank == 0:
-			uid.copy_(torch.frombuffer(bytearray(capi.comm_unique_id()), dtype=torch.uint8))
-		dist.broadcast(uid, 0)
-		model.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
+		from trlda_b200.distributed import init_comm
+		init_comm(model, dist, torch.device('cuda', local_rank))
 	capi.seed(1234 + rank)
 	stream = torch.cuda.ExternalStream(model.stream, device=torch.device('cuda', local_rank))
 	params = dict(w['params'])
@@ -345,7 +358,7 @@ def main():
 		'roofline': roofline}
 
 	if rank == 0 and world == 1 and not args.no_cpu_baseline:
-		sizes = [32, 96] if K >= 500 else [64, 200]
+		sizes = [64, min(512, B)]
 		cpu_value, full, spent, kind, text = cpu_sample(w, docs_np, lam0, sizes, args.workload)
 		line['cpu_baseline'] = {
 			'value': cpu_value, 'unit': 'docs/s', 'cores': int(os.environ.get('OMP_NUM_THREADS', os.cpu_count() or 1)),

@@ -10,8 +10,9 @@
 //   * tile columns are padded by 16 bytes so that BOTH passes are conflict-free 128-bit shared-memory loads:
 //       pass 1  acc_k  = sum_j W_j tile[j][k]      lanes along rows (4 floats / 2 doubles per lane), columns split
 //                                                  over thread groups and combined through shared memory
-//       pass 2  phi_j  = sum_k etheta_k tile[j][k]  one THREAD per column walking down its rows — no cross-lane
-//                                                  reduction at all (a quarter warp touches 8 x 16 B = all 32 banks)
+//       pass 2  phi_j  = sum_k etheta_k tile[j][k]  one THREAD per (column, row half) walking down its rows — no
+//                                                  cross-lane reduction at all (a quarter warp touches 8 x 16 B =
+//                                                  all 32 banks); the two row halves meet in shared memory
 //   * NO cluster barrier inside the fixed point: every CTA stages its partial phi-norms (and its share of
 //     sum|delta gamma|) in its own shared memory and sends the row to every CTA of the cluster with ONE
 //     DSMEM bulk copy per destination (`cp.async.bulk.shared::cluster.shared::cta`), which counts itself on
@@ -30,7 +31,7 @@ namespace cg = cooperative_groups;
 
 namespace trlda {
 
-constexpr int FAST_THREADS = 256;
+constexpr int FAST_THREADS = 384;   // 12 warps; two co-resident CTAs per SM still fit 85 registers per thread
 constexpr int FAST_WARPS = FAST_THREADS / 32;
 
 struct FastSmem {
@@ -120,7 +121,7 @@ __device__ __forceinline__ void vec_get(const float4& v, float (&o)[4]) { o[0] =
 __device__ __forceinline__ void vec_get(const double2& v, double (&o)[2]) { o[0] = v.x; o[1] = v.y; }
 
 template <typename T, bool CLUSTERED, bool USE_TMA>
-__global__ void __launch_bounds__(FAST_THREADS)
+__global__ void __launch_bounds__(FAST_THREADS, 2)
 k_estep_fast(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, int64_t doc_offset, int C, int kc, int n_cap) {
 	extern __shared__ __align__(128) unsigned char smem[];
 	using V = typename Vec<T>::type;
@@ -238,23 +239,36 @@ k_estep_fast(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, in
 			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
 				::"r"(bar_addr + 8 * (1 + buf)), "r"((uint32_t) C * row_bytes) : "memory");
 		T* stage = reinterpret_cast<T*>(pstage + (size_t) buf * row_bytes);
-		for(int j = tid; j < n; j += FAST_THREADS) {
-			const T* col = tile + (size_t) j * ld;
-			T acc0 = T(0), acc1 = T(0);
-			#pragma unroll 4
-			for(int r = 0; r < kc; r += 2 * VN) {
-				T e0[VN], v0[VN], e1[VN], v1[VN];
-				vec_get(*reinterpret_cast<const V*>(eth + r), e0);
-				vec_get(*reinterpret_cast<const V*>(col + r), v0);
-				vec_get(*reinterpret_cast<const V*>(eth + r + VN), e1);
-				vec_get(*reinterpret_cast<const V*>(col + r + VN), v1);
-				#pragma unroll
-				for(int q = 0; q < VN; ++q) {
-					acc0 = fma(e0[q], v0[q], acc0);
-					acc1 = fma(e1[q], v1[q], acc1);
+		// threads [0, NH) take the upper half of the rows of column tid, threads [NH, 2 NH) the lower half
+		constexpr int NH = FAST_THREADS / 2;
+		const int half = tid / NH, jt = tid % NH;
+		const int r_begin = half ? kc / 2 : 0, r_end = half ? kc : kc / 2;
+		for(int j0 = 0; j0 < n; j0 += NH) {
+			const int j = j0 + jt;
+			T part = T(0);
+			if(j < n) {
+				const T* col = tile + (size_t) j * ld;
+				T acc0 = T(0), acc1 = T(0);
+				#pragma unroll 4
+				for(int r = r_begin; r < r_end; r += 2 * VN) {
+					T e0[VN], v0[VN], e1[VN], v1[VN];
+					vec_get(*reinterpret_cast<const V*>(eth + r), e0);
+					vec_get(*reinterpret_cast<const V*>(col + r), v0);
+					vec_get(*reinterpret_cast<const V*>(eth + r + VN), e1);
+					vec_get(*reinterpret_cast<const V*>(col + r + VN), v1);
+					#pragma unroll
+					for(int q = 0; q < VN; ++q) {
+						acc0 = fma(e0[q], v0[q], acc0);
+						acc1 = fma(e1[q], v1[q], acc1);
+					}
 				}
+				part = acc0 + acc1;
+				if(half == 0)
+					stage[j] = part;
 			}
-			stage[j] = acc0 + acc1;
+			__syncthreads();
+			if(half == 1 && j < n)
+				stage[j] += part;
 		}
 		if(tid == 0)
 			*reinterpret_cast<double*>(pstage + (size_t) buf * row_bytes + (size_t) n_cap * sizeof(T)) = delta_part;

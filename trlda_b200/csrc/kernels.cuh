@@ -98,6 +98,12 @@ void launch_estep_fast(const EStepPlan& plan, const EStepArgs& args, const Devic
                        int64_t offset, int64_t count, int elem_size, cudaStream_t s);
 void configure_estep_fast(int smem_optin);
 
+// streaming kernel for warm-started documents (estep_stream.cu): one CTA per document, columns streamed through
+// per-warp cp.async rings, one sweep per inner iteration
+bool stream_estep_applicable(int K, int n_max, int elem_size, int smem_optin);
+void launch_estep_stream(const EStepArgs& args, const DeviceDocs& docs, const int32_t* order, int64_t offset,
+                         int64_t count, int n_max, int elem_size, cudaStream_t s);
+
 // segmented scatter.  If `fused`, lambda/beta are rebuilt in the same pass (single-GPU path); else the dense
 // K x V statistics are written to `sstats`.
 struct ScatterArgs {

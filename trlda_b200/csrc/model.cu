@@ -11,12 +11,14 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace trlda;
@@ -202,6 +204,13 @@ struct trlda_model {
 	struct Bucket { int64_t offset, count; int n_max; };
 	std::vector<Bucket> buckets;
 	bool force_generic = false;
+	// the length buckets of one E-step run concurrently on these streams (fork/join around the main stream), so
+	// that CTAs of buckets with different shared-memory footprints can share an SM and the buckets' tails overlap
+	static const int kAuxStreams = 3;
+	cudaStream_t aux[kAuxStreams] = {nullptr, nullptr, nullptr};
+	cudaEvent_t fork_event = nullptr, join_event[kAuxStreams] = {nullptr, nullptr, nullptr};
+	bool concurrent_buckets = true;
+	int stream_mode = 2;   // TRLDA_ESTEP_STREAM: 0 never use the streaming kernel, 1 only for warm-started E-steps, 2 always (default)
 	DevBuf ticks;    // debug phase timers of the fast E-step kernel (TRLDA_ESTEP_TICKS=1)
 	PinnedBuf staging, readback;
 	int64_t docs_total_count = 0;    // sum of all counts in the (global) minibatch
@@ -393,6 +402,12 @@ int upload_docs(trlda_model* m, const trlda_docs* docs) {
 	if(N > INT32_MAX)
 		return fail(m, TRLDA_ERR_ARG, "Too many (word, count) pairs in one minibatch.");
 
+	const bool host_timing = getenv("TRLDA_HOST_TIMING") != nullptr;
+	auto clock_now = [] { return std::chrono::steady_clock::now(); };
+	auto ms_since = [](std::chrono::steady_clock::time_point t0) {
+		return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+	};
+	const auto t_begin = clock_now();
 	// pinned staging: [doc_ptr | word_ids | counts | word_ptr | tok_doc | tok_src]
 	const size_t o_ptr = 0;
 	const size_t o_ids = o_ptr + sizeof(int64_t) * (B + 1);
@@ -414,15 +429,12 @@ int upload_docs(trlda_model* m, const trlda_docs* docs) {
 
 	// make sure the previous use of the staging buffer has been consumed
 	CUDA_TRY(m, cudaStreamSynchronize(m->stream));
+	const double t_sync = ms_since(t_begin);
 
 	if(B)
 		memcpy(s_ptr, docs->doc_ptr, sizeof(int64_t) * (B + 1));
 	else
 		s_ptr[0] = 0;
-	if(N) {
-		memcpy(s_ids, docs->word_ids, sizeof(int32_t) * N);
-		memcpy(s_cts, docs->counts, sizeof(int32_t) * N);
-	}
 	int n_max = 0;
 	int64_t total_count = 0;
 	for(int64_t d = 0; d < B; ++d) {
@@ -431,25 +443,67 @@ int upload_docs(trlda_model* m, const trlda_docs* docs) {
 			return fail(m, TRLDA_ERR_ARG, "Document offsets must be non-decreasing.");
 		n_max = std::max<int64_t>(n_max, n);
 	}
-	// stable counting sort of the tokens by word id
-	memset(s_wptr, 0, sizeof(int32_t) * ((size_t) V + 1));
-	for(int64_t t = 0; t < N; ++t) {
-		const int32_t w = s_ids[t];
-		if(w < 0 || w >= V)
-			return fail(m, TRLDA_ERR_ARG, "Word ID out of range.");
-		s_wptr[w + 1]++;
-		total_count += s_cts[t];
-	}
-	for(int w = 0; w < V; ++w)
-		s_wptr[w + 1] += s_wptr[w];
+	// stable counting sort of the tokens by word id, parallel over word ranges: thread t owns the words
+	// [V t / T, V (t+1) / T), scans the whole token stream in order and handles only its own words, so the
+	// order of a word's tokens (document order) does not depend on the number of threads
 	{
-		std::vector<int32_t> cursor(s_wptr, s_wptr + V);
-		for(int64_t d = 0; d < B; ++d)
-			for(int64_t t = s_ptr[d]; t < s_ptr[d + 1]; ++t) {
-				const int32_t pos = cursor[s_ids[t]]++;
-				s_tdoc[pos] = (int32_t) d;
-				s_tsrc[pos] = (int32_t) t;
+		const int T = (int) std::max(1u, std::min(8u, std::min(std::thread::hardware_concurrency(), (unsigned) (N / 65536 + 1))));
+		std::vector<int64_t> owned(T, 0), counts_sum(T, 0);
+		memset(s_wptr, 0, sizeof(int32_t) * ((size_t) V + 1));
+		const int32_t* ids = docs->word_ids;
+		const int32_t* cts = docs->counts;
+		auto range_of = [&](int t) { return std::make_pair((int32_t) ((int64_t) V * t / T), (int32_t) ((int64_t) V * (t + 1) / T)); };
+		auto run = [&](auto&& fn) {
+			std::vector<std::thread> pool;
+			for(int t = 1; t < T; ++t)
+				pool.emplace_back(fn, t);
+			fn(0);
+			for(auto& th : pool)
+				th.join();
+		};
+		run([&](int t) {
+			const auto r = range_of(t);
+			int64_t mine = 0, csum = 0;
+			// thread t also copies its slice of the id / count arrays into the pinned staging buffer
+			const int64_t c0 = N * t / T, c1 = N * (t + 1) / T;
+			if(c1 > c0) {
+				memcpy(s_ids + c0, ids + c0, sizeof(int32_t) * (c1 - c0));
+				memcpy(s_cts + c0, cts + c0, sizeof(int32_t) * (c1 - c0));
+				for(int64_t i = c0; i < c1; ++i)
+					csum += cts[i];
 			}
+			for(int64_t i = 0; i < N; ++i) {
+				const int32_t w = ids[i];
+				if(w >= r.first && w < r.second) {
+					s_wptr[w + 1]++;
+					++mine;
+				}
+			}
+			owned[t] = mine;
+			counts_sum[t] = csum;
+		});
+		int64_t seen = 0;
+		for(int t = 0; t < T; ++t) {
+			seen += owned[t];
+			total_count += counts_sum[t];
+		}
+		if(seen != N)
+			return fail(m, TRLDA_ERR_ARG, "Word ID out of range.");
+		for(int w = 0; w < V; ++w)
+			s_wptr[w + 1] += s_wptr[w];
+		std::vector<int32_t> cursor(s_wptr, s_wptr + V);
+		run([&](int t) {
+			const auto r = range_of(t);
+			for(int64_t d = 0; d < B; ++d)
+				for(int64_t i = s_ptr[d]; i < s_ptr[d + 1]; ++i) {
+					const int32_t w = ids[i];
+					if(w >= r.first && w < r.second) {
+						const int32_t pos = cursor[w]++;
+						s_tdoc[pos] = (int32_t) d;
+						s_tsrc[pos] = (int32_t) i;
+					}
+				}
+		});
 	}
 
 	// length buckets for the E-step: counting sort by length, longest first
@@ -482,6 +536,7 @@ int upload_docs(trlda_model* m, const trlda_docs* docs) {
 		}
 	}
 
+	const double t_host = ms_since(t_begin);
 	CUDA_TRY(m, m->b_order.ensure(sizeof(int32_t) * std::max<int64_t>(B, 1)));
 	CUDA_TRY(m, m->b_doc_ptr.ensure(sizeof(int64_t) * (B + 1)));
 	CUDA_TRY(m, m->b_word_ids.ensure(sizeof(int32_t) * std::max<int64_t>(N, 1)));
@@ -537,6 +592,9 @@ int upload_docs(trlda_model* m, const trlda_docs* docs) {
 	CUDA_TRY(m, m->doc_stat.ensure(kb));
 	CUDA_TRY(m, m->weight.ensure(sizeof(double) * std::max<int64_t>(N, 1)));
 	CUDA_TRY(m, m->iterations.ensure(sizeof(int32_t) * std::max<int64_t>(B, 1)));
+	if(host_timing)
+		fprintf(stderr, "[trlda] upload_docs: wait for stream %.2f ms, host packing (copy + counting sort + buckets) %.2f ms, total incl. H2D enqueue %.2f ms\n",
+		        t_sync, t_host - t_sync, ms_since(t_begin));
 	return TRLDA_OK;
 }
 
@@ -583,21 +641,54 @@ int run_estep(trlda_model* m, GammaSource src, const double* host_gamma, int max
 	a.max_iter = max_iter;
 	a.threshold = threshold;
 	a.ticks = m->ticks.as<unsigned long long>();
+	// Default path: the streaming kernel (estep_stream.cu).  Measured at cfg-3 it beats the cluster-resident kernel
+	// both for warm-started E-steps (one or two inner iterations: 2-3 sweeps) and for cold ones (the 126 MB L2
+	// serves the re-sweeps); the cluster kernels remain for shapes it does not cover (K too large for the per-lane
+	// register tile, unaligned K, very long documents)
+	const bool warm = src == GAMMA_KEEP;
+	if(!m->force_generic && m->docs.B > 0 && (m->stream_mode == 2 || (m->stream_mode == 1 && warm)) &&
+	   stream_estep_applicable(m->K, m->docs.n_max, m->beta_elem, m->smem_optin)) {
+		{
+			Launch l(m, KK_ESTEP);
+			launch_estep_stream(a, m->docs, m->b_order.as<int32_t>(), 0, m->docs.B, m->docs.n_max, m->beta_elem, m->stream);
+		}
+		m->gamma_valid = true;
+		m->stats.estep_docs = m->docs.B;
+		return check_launch(m, "estep_stream");
+	}
+	// fork: bucket i runs on stream i % (1 + kAuxStreams) (0 = the main stream); join before anything else continues
+	const bool fork = m->concurrent_buckets && m->buckets.size() > 1 && m->aux[0] != nullptr;
+	Launch span(m, KK_ESTEP);   // one timing span for the whole E-step (the bucket launches overlap)
+	m->stats.total_launches--;  // the span itself is not a kernel; the launches are counted below
+	if(fork) {
+		CUDA_TRY(m, cudaEventRecord(m->fork_event, m->stream));
+		for(int i = 0; i < trlda_model::kAuxStreams; ++i)
+			CUDA_TRY(m, cudaStreamWaitEvent(m->aux[i], m->fork_event, 0));
+	}
+	int index = 0;
 	for(const auto& bucket : m->buckets) {
+		const int lane = fork ? index % (1 + trlda_model::kAuxStreams) : 0;
+		cudaStream_t stream = lane == 0 ? m->stream : m->aux[lane - 1];
+		++index;
 		EStepPlan plan;
 		plan.cluster = 0;
 		if(!m->force_generic)
 			plan = plan_estep_fast(m->K, bucket.n_max, m->beta_elem, m->smem_optin, m->force_cluster);
-		Launch l(m, KK_ESTEP);
+		m->stats.total_launches++;
 		if(plan.cluster > 0) {
-			launch_estep_fast(plan, a, m->docs, m->b_order.as<int32_t>(), bucket.offset, bucket.count, m->beta_elem, m->stream);
+			launch_estep_fast(plan, a, m->docs, m->b_order.as<int32_t>(), bucket.offset, bucket.count, m->beta_elem, stream);
 		} else {
 			plan = plan_estep(m->K, bucket.n_max, m->beta_elem, m->smem_optin, m->force_cluster);
 			if(plan.n_cap < bucket.n_max || plan.smem > (size_t) m->smem_optin)
 				return fail(m, TRLDA_ERR_UNSUPPORTED, "A document has too many distinct words for the E-step kernel.");
-			launch_estep(plan, a, m->docs, m->b_order.as<int32_t>(), bucket.offset, bucket.count, m->beta_elem, m->stream);
+			launch_estep(plan, a, m->docs, m->b_order.as<int32_t>(), bucket.offset, bucket.count, m->beta_elem, stream);
 		}
 	}
+	if(fork)
+		for(int i = 0; i < trlda_model::kAuxStreams; ++i) {
+			CUDA_TRY(m, cudaEventRecord(m->join_event[i], m->aux[i]));
+			CUDA_TRY(m, cudaStreamWaitEvent(m->stream, m->join_event[i], 0));
+		}
 	m->gamma_valid = true;
 	m->stats.estep_docs = m->docs.B;
 	return check_launch(m, "estep");
@@ -1228,6 +1319,15 @@ int trlda_create(int kind, int num_words, int num_topics, int64_t num_documents,
 	}
 	configure_estep(m->smem_optin);
 	configure_estep_fast(m->smem_optin);
+	if(const char* sm = getenv("TRLDA_ESTEP_STREAM"))
+		m->stream_mode = atoi(sm);
+	if(const char* cb = getenv("TRLDA_CONCURRENT_BUCKETS"))
+		m->concurrent_buckets = atoi(cb) != 0;
+	cudaEventCreateWithFlags(&m->fork_event, cudaEventDisableTiming);
+	for(int i = 0; i < trlda_model::kAuxStreams; ++i) {
+		cudaStreamCreateWithFlags(&m->aux[i], cudaStreamNonBlocking);
+		cudaEventCreateWithFlags(&m->join_event[i], cudaEventDisableTiming);
+	}
 
 	int status = TRLDA_OK;
 	auto init = [&]() -> int {
@@ -1279,6 +1379,14 @@ void trlda_destroy(trlda_model* m) {
 		b->release();
 	m->staging.release();
 	m->readback.release();
+	for(int i = 0; i < trlda_model::kAuxStreams; ++i) {
+		if(m->aux[i])
+			cudaStreamDestroy(m->aux[i]);
+		if(m->join_event[i])
+			cudaEventDestroy(m->join_event[i]);
+	}
+	if(m->fork_event)
+		cudaEventDestroy(m->fork_event);
 	if(m->stream)
 		cudaStreamDestroy(m->stream);
 	delete m;
