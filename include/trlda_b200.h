@@ -184,7 +184,7 @@ TRLDA_API int trlda_get_row_sums(trlda_model* m, double* row_sums_K);   /* sum_w
 
 /* device special functions evaluated on n host values (test hook pinning the in-kernel psi / psi' / lgamma
  * against python/tests/utils_test.py:33-51): which = 0 digamma fp64, 1 trigamma fp64, 2 lgamma fp64,
- * 3 exp(digamma) as evaluated by the mixed-precision E-step. */
+ * 3 exp(digamma) as evaluated in mixed-precision mode, 4 exp(digamma) as evaluated in fp64 mode. */
 TRLDA_API int trlda_device_special(int device, int which, const double* x, int64_t n, double* out);
 
 /* host special functions used by the Newton steps: polygamma(n, x) of utils.cpp:107-111 (n = 0, 1, 2) */

@@ -45,6 +45,17 @@ def test_device_digamma_known_answers(capi):
 	assert np.allclose(tri, [10001.6212135283, 101.433299150792758, 7.275356590529597, 0.09516633568168575], rtol=1e-10)
 
 
+def test_device_exp_digamma_variants(capi):
+	"""the log-free exp(psi(x)) used by the kernels: the fp64-mode evaluation to a few ulp, the mixed-mode one
+	(recurrence to s >= 6, MUFU-seeded reciprocal) far inside the float32 rounding it feeds"""
+	case = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'special.npz'))
+	x = case['x'][case['x'] > 1e-3]
+	want = np.exp(case['digamma'][case['x'] > 1e-3])
+	ok = want > 1e-300
+	assert np.max(np.abs(capi.device_special(4, x)[ok] - want[ok]) / want[ok]) < 5e-13
+	assert np.max(np.abs(capi.device_special(3, x)[ok] - want[ok]) / want[ok]) < 1e-10
+
+
 # ---- E-step ----------------------------------------------------------------------------------------------------------
 ESTEP_SHAPES = [
 	# K, V, B, max_len, max_iter

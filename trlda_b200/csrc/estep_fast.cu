@@ -215,7 +215,7 @@ k_estep_fast(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, in
 				tile[(size_t) j * ld + r] = T(0);
 	// gamma0 slice and exp(psi(gamma0)) while the copies are in flight (lda.cpp:174)
 	if(tid < kc) {
-		const double e = tid < kn ? exp_digamma(g0_early) : 0.0;
+		const double e = tid < kn ? exp_digamma_for<T>(g0_early, 0.0) : 0.0;
 		gam[tid] = g0_early;
 		eth[tid] = (T) e;
 	}
@@ -356,7 +356,7 @@ k_estep_fast(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, in
 			g_new += a.alpha[k0 + tid];
 			delta_local = fabs(g_old - g_new);
 			gam[tid] = g_new;
-			eth[tid] = (T) exp_digamma(g_new);
+			eth[tid] = (T) exp_digamma_for<T>(g_new, 0.0);
 		}
 		// block sum of |delta gamma| (the barrier also orders the eth writes before pass 2)
 		delta_local = warp_sum(delta_local);

@@ -53,7 +53,7 @@ __host__ __device__ inline StreamSmem stream_smem_layout(int NW, int kp, int n_c
 	return L;
 }
 
-static int g_stream_warps_f32 = 16;   // TRLDA_STREAM_WARPS: 16 (one CTA per SM) or 8 (two)
+static int g_stream_warps_f32 = 8;    // TRLDA_STREAM_WARPS: 8 (two CTAs per SM, default) or 16 (one)
 static inline int stream_warps(int elem) { return elem == 4 ? g_stream_warps_f32 : 8; }
 static inline int stream_nvec(int K, int elem) {
 	const int per_sweep = 32 * (16 / elem);
@@ -108,7 +108,7 @@ k_estep_stream(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, 
 		double g = 0.0, e = 0.0;
 		if(r < K) {
 			g = a.gamma[d * K + r];
-			e = exp_digamma(g);                                   // lda.cpp:174
+			e = exp_digamma_for<T>(g, 0.0);                                   // lda.cpp:174
 		}
 		gam[r] = g;
 		eth[r] = (T) e;
@@ -131,6 +131,8 @@ k_estep_stream(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, 
 
 	int it = 0;
 	bool converged = false;
+	bool primed = false;   // the ring already holds the first columns of the coming sweep
+	int stage = 0;
 	while(true) {
 		const bool final_sweep = converged || it >= a.max_iter;
 		// ---- one sweep over the document's columns: this warp takes columns warp, warp + NW, ... -----------------------
@@ -142,15 +144,23 @@ k_estep_stream(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, 
 			for(int q = 0; q < VN; ++q)
 				acc[v][q] = T(0);
 		}
-		#pragma unroll
-		for(int s = 0; s < STREAM_DEPTH; ++s) {
-			const int j = warp + s * NW;
-			if(j < n)
-				issue(j, s);
-			asm volatile("cp.async.commit_group;" ::: "memory");
+		// M = number of columns of this warp.  If the ring was not primed by the previous sweep, fill it now.
+		const int M = warp < n ? (n - warp + NW - 1) / NW : 0;
+		if(!primed) {
+			#pragma unroll
+			for(int s = 0; s < STREAM_DEPTH; ++s) {
+				if(s < M)
+					issue(warp + s * NW, s);
+				asm volatile("cp.async.commit_group;" ::: "memory");
+			}
+			stage = 0;
 		}
-		int stage = 0;
-		for(int j = warp; j < n; j += NW) {
+		// a non-final sweep is always followed by another one over the same columns: its first STREAM_DEPTH columns
+		// are requested while the tail of this sweep is consumed, so the ring never drains at a sweep boundary and
+		// the (L2) latency of the next sweep hides behind the reduction and the psi evaluations
+		const bool prime_next = !final_sweep && M >= STREAM_DEPTH;
+		for(int mcol = 0; mcol < M; ++mcol) {
+			const int j = warp + mcol * NW;
 			asm volatile("cp.async.wait_group %0;" ::"n"(STREAM_DEPTH - 1) : "memory");
 			__syncwarp();
 			const T* col = my_ring + (size_t) stage * KP;
@@ -181,13 +191,17 @@ k_estep_stream(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, 
 			if(final_sweep && lane == 0)
 				a.weight[begin + j] = (double) wt;
 			__syncwarp();
-			const int jn = j + STREAM_DEPTH * NW;
-			if(jn < n)
-				issue(jn, stage);
+			const int mn = mcol + STREAM_DEPTH;
+			if(mn < M)
+				issue(warp + mn * NW, stage);
+			else if(prime_next)
+				issue(warp + (mn - M) * NW, stage);
 			asm volatile("cp.async.commit_group;" ::: "memory");
 			stage = stage + 1 == STREAM_DEPTH ? 0 : stage + 1;
 		}
-		asm volatile("cp.async.wait_group 0;" ::: "memory");
+		primed = prime_next;
+		if(!primed)
+			asm volatile("cp.async.wait_group 0;" ::: "memory");
 		// ---- the per-warp partial sums meet in shared memory, fixed order ------------------------------------------------
 		#pragma unroll
 		for(int v = 0; v < NVEC; ++v) {
@@ -218,7 +232,7 @@ k_estep_stream(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, 
 				g_new += a.alpha[r];
 				delta_local += fabs(g_old - g_new);
 				gam[r] = g_new;
-				eth[r] = (T) exp_digamma(g_new);
+				eth[r] = (T) exp_digamma_for<T>(g_new, 0.0);
 			}
 		}
 		if(final_sweep)
@@ -250,7 +264,7 @@ void launch_estep_stream(const EStepArgs& args, const DeviceDocs& docs, const in
 	if(count == 0)
 		return;
 	if(const char* e = getenv("TRLDA_STREAM_WARPS"))
-		g_stream_warps_f32 = atoi(e) == 8 ? 8 : 16;
+		g_stream_warps_f32 = atoi(e) == 16 ? 16 : 8;
 	const int nvec = stream_nvec(args.K, elem_size);
 	const int n_cap = std::max(32, (n_max + 31) / 32 * 32);
 	const int kp = nvec * 32 * (16 / elem_size);

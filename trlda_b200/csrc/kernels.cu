@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(256) k_beta_prep(const double* __restrict__ la
 				psum += p;
 				beta[i] = (T) exp(p - psi_rows[k]);
 			} else {
-				beta[i] = (T) exp_digamma_shifted(lambda[i], psi_rows[k]);
+				beta[i] = (T) exp_digamma_for<T>(lambda[i], psi_rows[k]);
 			}
 		}
 		if(psi_partials) {
@@ -603,8 +603,144 @@ __global__ void __launch_bounds__(SCATTER_THREADS, (KPT <= 8 ? 7 : 1)) k_scatter
 				if(a.write_beta)
 					__stcs(beta + e, (TB) exp(p - a.psi_rows[k]));
 			} else if(a.write_beta) {
-				__stcs(beta + e, (TB) exp_digamma_shifted(lam, a.psi_rows[k]));
+				__stcs(beta + e, (TB) exp_digamma_for<TB>(lam, a.psi_rows[k]));
 			}
+		}
+		if(a.fused && a.psi_partials) {
+			const double total = block_sum(psum, scratch);
+			if(threadIdx.x == 0)
+				a.psi_partials[w] = total;
+		}
+	}
+}
+
+// Vectorised variant for the mixed-precision path (etheta and beta in float32, K a multiple of 4): every thread
+// owns NCH chunks of 4 consecutive topics, so a token costs NCH 128-bit L2 loads per thread instead of 4 NCH
+// 32-bit ones, and lambda' / lambda / beta move as 128-/256-bit streaming accesses.
+template <int NT, int NCH, int G>
+__global__ void __launch_bounds__(NT, (NT == 128 && NCH <= 2 ? 5 : 1)) k_scatter_vec(ScatterArgs a, DeviceDocs docs) {
+	__shared__ double scratch[32];
+	const int K = a.K;
+	const int chunks = K / 4;
+	const float* __restrict__ etheta = static_cast<const float*>(a.etheta);
+	float* beta = static_cast<float*>(a.beta);
+	const bool need_prime = a.fused && a.coef.mode != MSTEP_BATCH;
+	// exp(-psi(new row sum)) of this thread's topics, prepared once (the thread keeps the same topics for all words)
+	float ek[NCH][4];
+	#pragma unroll
+	for(int i = 0; i < NCH; ++i) {
+		const int c = threadIdx.x + i * NT;
+		#pragma unroll
+		for(int q = 0; q < 4; ++q)
+			ek[i][q] = (a.fused && a.write_beta && c < chunks) ? (float) exp(-a.psi_rows[4 * c + q]) : 0.0f;
+	}
+	for(int w = blockIdx.x; w < a.V; w += gridDim.x) {
+		const int64_t base = (int64_t) w * K;
+		float4 bcol[NCH];
+		double lp[NCH][4];
+		#pragma unroll
+		for(int i = 0; i < NCH; ++i) {
+			const int c = threadIdx.x + i * NT;
+			bcol[i] = c < chunks ? __ldcs(reinterpret_cast<const float4*>(beta + base) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+			if(c < chunks && need_prime) {
+				const double2 p0 = __ldcs(reinterpret_cast<const double2*>(a.lambda_prime + base) + 2 * c);
+				const double2 p1 = __ldcs(reinterpret_cast<const double2*>(a.lambda_prime + base) + 2 * c + 1);
+				lp[i][0] = p0.x; lp[i][1] = p0.y; lp[i][2] = p1.x; lp[i][3] = p1.y;
+			} else {
+				lp[i][0] = lp[i][1] = lp[i][2] = lp[i][3] = 0.0;
+			}
+		}
+		double acc[NCH][4];
+		#pragma unroll
+		for(int i = 0; i < NCH; ++i)
+			acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.0;
+
+		const int t0 = docs.word_ptr[w], t1 = docs.word_ptr[w + 1];
+		int dd[G];
+		double ww[G];
+		auto fetch = [&](int t) {
+			#pragma unroll
+			for(int u = 0; u < G; ++u) {
+				const bool ok = t + u < t1;
+				dd[u] = ok ? docs.tok_doc[t + u] : 0;
+				ww[u] = ok ? a.weight[docs.tok_src[t + u]] : 0.0;
+			}
+		};
+		if(t0 < t1)
+			fetch(t0);
+		for(int t = t0; t < t1; t += G) {
+			float4 v[G][NCH];
+			#pragma unroll
+			for(int u = 0; u < G; ++u) {
+				const float4* col = reinterpret_cast<const float4*>(etheta + (int64_t) dd[u] * K);
+				#pragma unroll
+				for(int i = 0; i < NCH; ++i) {
+					const int c = threadIdx.x + i * NT;
+					v[u][i] = c < chunks ? col[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+				}
+			}
+			double wc[G];
+			#pragma unroll
+			for(int u = 0; u < G; ++u)
+				wc[u] = ww[u];
+			if(t + G < t1)
+				fetch(t + G);
+			// float32 products summed over the <= G tokens of the group, float64 across groups
+			#pragma unroll
+			for(int i = 0; i < NCH; ++i) {
+				float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
+				#pragma unroll
+				for(int u = 0; u < G; ++u) {
+					const float wf = (float) wc[u];
+					g0 = fmaf(wf, v[u][i].x, g0);
+					g1 = fmaf(wf, v[u][i].y, g1);
+					g2 = fmaf(wf, v[u][i].z, g2);
+					g3 = fmaf(wf, v[u][i].w, g3);
+				}
+				acc[i][0] += (double) g0;
+				acc[i][1] += (double) g1;
+				acc[i][2] += (double) g2;
+				acc[i][3] += (double) g3;
+			}
+		}
+
+		double psum = 0.0;
+		#pragma unroll
+		for(int i = 0; i < NCH; ++i) {
+			const int c = threadIdx.x + i * NT;
+			if(c >= chunks)
+				continue;
+			const float bv[4] = {bcol[i].x, bcol[i].y, bcol[i].z, bcol[i].w};
+			double lam[4];
+			float bnew[4];
+			#pragma unroll
+			for(int q = 0; q < 4; ++q) {
+				const double s = acc[i][q] * (double) bv[q];                 // lda.cpp:217
+				lam[q] = a.fused ? mstep_value(a.coef, lp[i][q], s) : s;
+			}
+			if(!a.fused) {
+				double2* out = reinterpret_cast<double2*>(a.sstats + base) + 2 * c;
+				out[0] = make_double2(lam[0], lam[1]);
+				out[1] = make_double2(lam[2], lam[3]);
+				continue;
+			}
+			double2* out = reinterpret_cast<double2*>(a.lambda + base) + 2 * c;
+			__stcs(out, make_double2(lam[0], lam[1]));
+			__stcs(out + 1, make_double2(lam[2], lam[3]));
+			if(a.psi_partials) {
+				#pragma unroll
+				for(int q = 0; q < 4; ++q) {
+					const double p = digamma(lam[q]);
+					psum += p;
+					bnew[q] = (float) exp(p - a.psi_rows[4 * c + q]);
+				}
+			} else if(a.write_beta) {
+				#pragma unroll
+				for(int q = 0; q < 4; ++q)
+					bnew[q] = exp_digamma_scaled_f32(lam[q], ek[i][q]);
+			}
+			if(a.write_beta)
+				__stcs(reinterpret_cast<float4*>(beta + base) + c, make_float4(bnew[0], bnew[1], bnew[2], bnew[3]));
 		}
 		if(a.fused && a.psi_partials) {
 			const double total = block_sum(psum, scratch);
@@ -627,6 +763,15 @@ static void launch_scatter_t(const ScatterArgs& a, const DeviceDocs& docs, cudaS
 }
 
 void launch_scatter(const ScatterArgs& a, const DeviceDocs& docs, cudaStream_t s) {
+	if(a.etheta_elem == 4 && a.beta_elem == 4 && a.K % 4 == 0 && a.K <= 4096) {
+		const int grid = std::min(a.V, 148 * 64);
+		const int chunks = a.K / 4;
+		if(chunks <= 128) k_scatter_vec<128, 1, 4><<<grid, 128, 0, s>>>(a, docs);
+		else if(chunks <= 256) k_scatter_vec<128, 2, 4><<<grid, 128, 0, s>>>(a, docs);
+		else if(chunks <= 512) k_scatter_vec<256, 2, 4><<<grid, 256, 0, s>>>(a, docs);
+		else k_scatter_vec<256, 4, 2><<<grid, 256, 0, s>>>(a, docs);
+		return;
+	}
 	if(a.etheta_elem == 8 && a.beta_elem == 8) launch_scatter_t<double, double>(a, docs, s);
 	else if(a.etheta_elem == 4 && a.beta_elem == 4) launch_scatter_t<float, float>(a, docs, s);
 	else if(a.etheta_elem == 8 && a.beta_elem == 4) launch_scatter_t<double, float>(a, docs, s);
@@ -653,7 +798,7 @@ __global__ void __launch_bounds__(256) k_mstep(MStepArgs a) {
 				if(a.write_beta)
 					beta[e] = (TB) exp(p - a.psi_rows[k]);
 			} else if(a.write_beta) {
-				beta[e] = (TB) exp_digamma_shifted(lam, a.psi_rows[k]);
+				beta[e] = (TB) exp_digamma_for<TB>(lam, a.psi_rows[k]);
 			}
 		}
 		if(a.psi_partials) {
@@ -699,7 +844,7 @@ __global__ void __launch_bounds__(256) k_init_update(int K, int V, double rho, d
 			const int64_t e = (int64_t) w * K + k;
 			const double lam = (1. - rho) * lambda_prime[e] + target;   // onlinelda.cpp:85
 			lambda[e] = lam;
-			beta[e] = (TB) exp_digamma_shifted(lam, psi_rows[k]);
+			beta[e] = (TB) exp_digamma_for<TB>(lam, psi_rows[k]);
 		}
 	}
 }
@@ -972,7 +1117,8 @@ __global__ void k_special(int which, const double* __restrict__ x, int64_t n, do
 		case 0: r = digamma(v); break;
 		case 1: r = trigamma(v); break;
 		case 2: r = lgamma(v); break;
-		default: r = (double) exp_digamma_f32((float) v); break;
+		case 3: r = exp_digamma_shifted_mixed(v, 0.0); break;
+		default: r = exp_digamma_shifted(v, 0.0); break;
 	}
 	out[i] = r;
 }

@@ -91,6 +91,61 @@ __device__ __forceinline__ double exp_digamma(double x) {
 	return exp_digamma_shifted(x, 0.0);
 }
 
+// Same quantity for the MIXED-precision mode, where the result is rounded to float32 anyway: the recurrence stops
+// at s >= 6 (the 7-term series is then still good to ~2e-13 absolute in psi) and the one reciprocal is a float32
+// MUFU seed refined by two fp64 Newton steps (relative error ~1e-16) instead of a full fp64 division.
+__device__ __forceinline__ double exp_digamma_shifted_mixed(double x, double c) {
+	if(x <= 0.0)
+		return exp(digamma_reflect(x) - c);
+	double num = 0.0, den = 1.0, s = x;
+	#pragma unroll 1
+	while(s < 6.0) {
+		num = fma(num, s, den);
+		den *= s;
+		s += 1.0;
+	}
+	const double y = s * den;
+	double q;
+	if(y > 1e-30 && y < 1e30) {
+		q = (double) __frcp_rn((float) y);
+		q = fma(q, fma(-y, q, 1.0), q);
+		q = fma(q, fma(-y, q, 1.0), q);
+	} else {
+		q = 1.0 / y;
+	}
+	const double r = den * q;
+	const double t = fma(num, s, 0.5 * den) * q;
+	return s * exp(-(t + psi_series(r * r) + c));
+}
+
+// expElogbeta element for the MIXED mode, evaluated in float32: beta = exp(psi(lambda)) * ek with ek = exp(-psi(row sum))
+// prepared once per topic.  Same decomposition (recurrence to s >= 6, one reciprocal, three series terms — the
+// fourth is 2.5e-9 at s = 6); relative error ~5e-7, consistent with the float32 storage and the float32 inner
+// products of this mode.  Arguments outside the float32 range of the recurrence take the fp64 path.
+__device__ __forceinline__ float exp_digamma_scaled_f32(double lambda, float ek) {
+	const float x = (float) lambda;
+	if(!(x > 1e-30f) || x > 1e30f)
+		return (float) (exp_digamma_shifted_mixed(lambda, 0.0) * (double) ek);
+	float num = 0.0f, den = 1.0f, s = x;
+	#pragma unroll 1
+	while(s < 6.0f) {
+		num = fmaf(num, s, den);
+		den *= s;
+		s += 1.0f;
+	}
+	const float q = __frcp_rn(s * den);
+	const float r = den * q;
+	const float t = fmaf(num, s, 0.5f * den) * q;
+	const float z = r * r;
+	const float y = z * (8.33333333333e-2f - z * (8.33333333333e-3f - z * 3.96825396825e-3f));
+	return s * expf(-(t + y)) * ek;
+}
+
+// picks the evaluation matching the element type of the expElogbeta working copy
+template <typename T> __device__ __forceinline__ double exp_digamma_for(double x, double c);
+template <> __device__ __forceinline__ double exp_digamma_for<double>(double x, double c) { return exp_digamma_shifted(x, c); }
+template <> __device__ __forceinline__ double exp_digamma_for<float>(double x, double c) { return exp_digamma_shifted_mixed(x, c); }
+
 // psi'(x) = zeta(2, x) for x > 0: shift to s >= 10 by the recurrence psi'(x) = psi'(x+1) + 1/x^2, then the
 // asymptotic series 1/s + 1/(2 s^2) + sum B_2k / s^(2k+1).  Only K+1 values per alpha update are needed
 // (onlinelda.cpp:132-133), so clarity beats speed here.
@@ -110,28 +165,6 @@ __host__ __device__ __forceinline__ double trigamma(double x) {
 	p = fma(p, z, -1.0 / 30.0);
 	p = fma(p, z, 1.0 / 6.0);
 	return w + r + 0.5 * z + p * z * r;
-}
-
-// ---- float32 variants for the mixed-precision E-step ---------------------------------------------------------
-
-// exp(psi(x)) evaluated in float32 arithmetic for x > 0.  Same decomposition; the series is truncated to
-// the three terms float32 can resolve at s >= 6, and the shift point is lowered to 6 accordingly.
-__device__ __forceinline__ float exp_digamma_f32(float x) {
-	float num = 0.0f, den = 1.0f, s = x;
-	#pragma unroll 1
-	while(s < 6.0f) {
-		num = fmaf(num, s, den);
-		den *= s;
-		s += 1.0f;
-	}
-	const float r = __frcp_rn(s);
-	const float z = r * r;
-	float p = -3.96825396825e-3f;               // -B6/6
-	p = fmaf(p, z, 8.33333333333e-3f);          //  -B4/4 -> sign folded below
-	p = fmaf(p, z, -8.33333333333e-2f);         // -B2/2
-	// psi = log(s) - r/2 + z*p - num/den
-	const float psi = logf(s) - 0.5f * r + z * p - __fdividef(num, den);
-	return expf(psi);
 }
 
 // ---- warp / block reductions ---------------------------------------------------------------------------------
