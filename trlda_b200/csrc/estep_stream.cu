@@ -76,7 +76,7 @@ bool stream_estep_applicable(int K, int n_max, int elem, int smem_optin) {
 }
 
 template <typename T, int NW, int NVEC>
-__global__ void __launch_bounds__(NW * 32, (NW * 32 * NVEC * 16 <= 32768 ? 2 : 1))
+__global__ void __launch_bounds__(NW * 32, (NW == 4 ? 3 : (NW == 8 && sizeof(T) == 4 ? 2 : 1)))
 k_estep_stream(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, int64_t doc_offset, int n_cap) {
 	extern __shared__ __align__(128) unsigned char smem[];
 	using V = typename SVec<T>::type;
@@ -264,7 +264,7 @@ void launch_estep_stream(const EStepArgs& args, const DeviceDocs& docs, const in
 	if(count == 0)
 		return;
 	if(const char* e = getenv("TRLDA_STREAM_WARPS"))
-		g_stream_warps_f32 = atoi(e) == 16 ? 16 : 8;
+		g_stream_warps_f32 = atoi(e) == 16 ? 16 : (atoi(e) == 4 ? 4 : 8);
 	const int nvec = stream_nvec(args.K, elem_size);
 	const int n_cap = std::max(32, (n_max + 31) / 32 * 32);
 	const int kp = nvec * 32 * (16 / elem_size);
@@ -275,6 +275,13 @@ void launch_estep_stream(const EStepArgs& args, const DeviceDocs& docs, const in
 			case 2: launch_stream_t<float, 16, 2>(args, docs, order, offset, count, n_cap, smem, s); break;
 			case 4: launch_stream_t<float, 16, 4>(args, docs, order, offset, count, n_cap, smem, s); break;
 			default: launch_stream_t<float, 16, 8>(args, docs, order, offset, count, n_cap, smem, s); break;
+		}
+	} else if(elem_size == 4 && stream_warps(4) == 4) {
+		switch(nvec) {
+			case 1: launch_stream_t<float, 4, 1>(args, docs, order, offset, count, n_cap, smem, s); break;
+			case 2: launch_stream_t<float, 4, 2>(args, docs, order, offset, count, n_cap, smem, s); break;
+			case 4: launch_stream_t<float, 4, 4>(args, docs, order, offset, count, n_cap, smem, s); break;
+			default: launch_stream_t<float, 4, 8>(args, docs, order, offset, count, n_cap, smem, s); break;
 		}
 	} else if(elem_size == 4) {
 		switch(nvec) {
