@@ -719,9 +719,13 @@ __global__ void __launch_bounds__(NT, (NT == 128 && NCH <= 2 ? 5 : 1)) k_scatter
 				lam[q] = a.fused ? mstep_value(a.coef, lp[i][q], s) : s;
 			}
 			if(!a.fused) {
-				double2* out = reinterpret_cast<double2*>(a.sstats + base) + 2 * c;
-				out[0] = make_double2(lam[0], lam[1]);
-				out[1] = make_double2(lam[2], lam[3]);
+				if(a.sstats32) {
+					reinterpret_cast<float4*>(a.sstats32 + base)[c] = make_float4((float) lam[0], (float) lam[1], (float) lam[2], (float) lam[3]);
+				} else {
+					double2* out = reinterpret_cast<double2*>(a.sstats + base) + 2 * c;
+					out[0] = make_double2(lam[0], lam[1]);
+					out[1] = make_double2(lam[2], lam[3]);
+				}
 				continue;
 			}
 			double2* out = reinterpret_cast<double2*>(a.lambda + base) + 2 * c;
@@ -814,6 +818,117 @@ void launch_mstep(const MStepArgs& a, cudaStream_t s) {
 	const int grid = std::min(a.V, 148 * 16);
 	if(a.beta_elem == 8) k_mstep<double><<<grid, block, 0, s>>>(a);
 	else k_mstep<float><<<grid, block, 0, s>>>(a);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// sharded M-step over NVLink peer memory (see kernels.cuh)
+// ------------------------------------------------------------------------------------------------------------
+template <typename TB, typename TS>
+__global__ void __launch_bounds__(256) k_mstep_shard(ShardMStepArgs a) {
+	__shared__ double scratch[32];
+	const int K = a.K, G = a.nranks;
+	const int chunks = K / 4;
+	// exp(-psi(new row sum)) of this thread's first chunk of topics (the only one when K <= 4 * blockDim)
+	float ek0[4] = {0.f, 0.f, 0.f, 0.f};
+	if(sizeof(TB) == 4 && a.write_beta && !a.psi_partials && (int) threadIdx.x < chunks)
+		for(int q = 0; q < 4; ++q)
+			ek0[q] = (float) exp(-a.psi_rows[4 * threadIdx.x + q]);
+	for(int w = a.v0 + blockIdx.x; w < a.v1; w += gridDim.x) {
+		const int64_t base = (int64_t) w * K;
+		double psum = 0.0;
+		for(int c = threadIdx.x; c < chunks; c += blockDim.x) {
+			float ek[4];
+			#pragma unroll
+			for(int q = 0; q < 4; ++q)
+				ek[q] = c == (int) threadIdx.x ? ek0[q] : ((sizeof(TB) == 4 && a.write_beta && !a.psi_partials) ? (float) exp(-a.psi_rows[4 * c + q]) : 0.f);
+			// pull: all ranks' partial columns in flight at once, summed in rank order (deterministic)
+			double s4[4] = {0.0, 0.0, 0.0, 0.0};
+			if constexpr(sizeof(TS) == 8) {
+				double2 part[TRLDA_MAX_RANKS][2];
+				#pragma unroll
+				for(int r = 0; r < TRLDA_MAX_RANKS; ++r)
+					if(r < G) {
+						const double2* src = reinterpret_cast<const double2*>(static_cast<const double*>(a.sstats[r]) + base) + 2 * c;
+						part[r][0] = src[0];
+						part[r][1] = src[1];
+					}
+				#pragma unroll
+				for(int r = 0; r < TRLDA_MAX_RANKS; ++r)
+					if(r < G) {
+						s4[0] += part[r][0].x; s4[1] += part[r][0].y; s4[2] += part[r][1].x; s4[3] += part[r][1].y;
+					}
+			} else {
+				float4 part[TRLDA_MAX_RANKS];
+				#pragma unroll
+				for(int r = 0; r < TRLDA_MAX_RANKS; ++r)
+					if(r < G)
+						part[r] = reinterpret_cast<const float4*>(static_cast<const float*>(a.sstats[r]) + base)[c];
+				#pragma unroll
+				for(int r = 0; r < TRLDA_MAX_RANKS; ++r)
+					if(r < G) {
+						s4[0] += (double) part[r].x; s4[1] += (double) part[r].y; s4[2] += (double) part[r].z; s4[3] += (double) part[r].w;
+					}
+			}
+			double lp[4] = {0.0, 0.0, 0.0, 0.0};
+			if(a.coef.mode != MSTEP_BATCH) {
+				const double2 p0 = __ldcs(reinterpret_cast<const double2*>(a.lambda_prime + base) + 2 * c);
+				const double2 p1 = __ldcs(reinterpret_cast<const double2*>(a.lambda_prime + base) + 2 * c + 1);
+				lp[0] = p0.x; lp[1] = p0.y; lp[2] = p1.x; lp[3] = p1.y;
+			}
+			double lam[4];
+			TB bnew[4];
+			#pragma unroll
+			for(int q = 0; q < 4; ++q) {
+				lam[q] = mstep_value(a.coef, lp[q], s4[q]);
+				if(a.psi_partials) {
+					const double p = digamma(lam[q]);
+					psum += p;
+					bnew[q] = (TB) exp(p - a.psi_rows[4 * c + q]);
+				} else if(a.write_beta) {
+					if constexpr(sizeof(TB) == 4)
+						bnew[q] = exp_digamma_scaled_f32(lam[q], ek[q]);
+					else
+						bnew[q] = (TB) exp_digamma_for<TB>(lam[q], a.psi_rows[4 * c + q]);
+				}
+			}
+			// push: the new columns go to every rank's replica
+			#pragma unroll
+			for(int r = 0; r < TRLDA_MAX_RANKS; ++r)
+				if(r < G) {
+					if(r == a.rank || a.broadcast_lambda) {
+						double2* out = reinterpret_cast<double2*>(a.lambda[r] + base) + 2 * c;
+						out[0] = make_double2(lam[0], lam[1]);
+						out[1] = make_double2(lam[2], lam[3]);
+					}
+					if(a.write_beta) {
+						TB* out = static_cast<TB*>(a.beta[r]) + base + 4 * c;
+						if constexpr(sizeof(TB) == 4) {
+							*reinterpret_cast<float4*>(out) = make_float4(bnew[0], bnew[1], bnew[2], bnew[3]);
+						} else {
+							reinterpret_cast<double2*>(out)[0] = make_double2(bnew[0], bnew[1]);
+							reinterpret_cast<double2*>(out)[1] = make_double2(bnew[2], bnew[3]);
+						}
+					}
+				}
+		}
+		if(a.psi_partials) {
+			const double total = block_sum(psum, scratch);
+			if(threadIdx.x == 0)
+				a.psi_partials[w] = total;
+		}
+	}
+}
+
+void launch_mstep_shard(const ShardMStepArgs& a, cudaStream_t s) {
+	const int words = a.v1 - a.v0;
+	if(words <= 0)
+		return;
+	const int block = std::min(256, std::max(32, round_up(a.K / 4, 32)));
+	const int grid = std::min(words, 148 * 8);
+	if(a.beta_elem == 8 && a.sstats_elem == 8) k_mstep_shard<double, double><<<grid, block, 0, s>>>(a);
+	else if(a.beta_elem == 4 && a.sstats_elem == 4) k_mstep_shard<float, float><<<grid, block, 0, s>>>(a);
+	else if(a.beta_elem == 4) k_mstep_shard<float, double><<<grid, block, 0, s>>>(a);
+	else k_mstep_shard<double, float><<<grid, block, 0, s>>>(a);
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -114,6 +114,7 @@ struct ScatterArgs {
 	void* beta = nullptr;             // K x V in (old) / out (new, if write_beta)
 	int beta_elem = 8;
 	double* sstats = nullptr;         // dense output (unfused)
+	float* sstats32 = nullptr;        // dense output rounded to float32 (mixed-mode exchange between GPUs), instead of sstats
 	// fused part
 	bool fused = false;
 	MStepCoef coef{};
@@ -138,6 +139,27 @@ struct MStepArgs {
 	double* psi_partials = nullptr;
 };
 void launch_mstep(const MStepArgs& a, cudaStream_t s);
+
+// Multi-GPU M-step over NVLink peer memory: this rank owns the words [v0, v1).  For each of them the kernel PULLS the
+// partial sufficient statistics of every rank (peer loads), sums them in rank order, blends with lambda', and PUSHES
+// the new expElogbeta column (and, on request, the new lambda column) into every rank's replica (peer stores):
+// reduce-scatter + M-step + beta-prep + all-gather in one kernel, no intermediate K x V buffer, no NCCL on the data.
+constexpr int TRLDA_MAX_RANKS = 8;    // one NVSwitch node
+struct ShardMStepArgs {
+	int K = 0, V = 0, v0 = 0, v1 = 0, nranks = 1, rank = 0;
+	MStepCoef coef{};
+	const void* sstats[TRLDA_MAX_RANKS] = {};     // every rank's local dense statistics (peer-mapped), float64 or float32
+	int sstats_elem = 8;
+	void* beta[TRLDA_MAX_RANKS] = {};             // every rank's expElogbeta replica
+	double* lambda[TRLDA_MAX_RANKS] = {};         // every rank's target lambda buffer
+	const double* lambda_prime = nullptr;         // local
+	const double* psi_rows = nullptr;
+	int beta_elem = 8;
+	bool write_beta = false;
+	bool broadcast_lambda = false;                // write lambda to all ranks (else only to this rank's replica)
+	double* psi_partials = nullptr;               // V values, this rank fills [v0, v1)
+};
+void launch_mstep_shard(const ShardMStepArgs& a, cudaStream_t s);
 
 // lambda = (1-rho) lambda' + rho (eta + scale_k * wordcount_w), then beta-prep (onlinelda.cpp:79-86)
 void launch_init_update(const DeviceDocs& docs, int K, int V, double rho, double eta, double scale_k,

@@ -101,6 +101,7 @@ struct NcclApi {
 	ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
 	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
 	ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
 	const char* (*GetErrorString)(ncclResult_t) = nullptr;
 	bool ok = false;
 };
@@ -122,7 +123,8 @@ NcclApi& nccl_api() {
 		api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(api.handle, "ncclCommDestroy"));
 		api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(api.handle, "ncclAllReduce"));
 		api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(api.handle, "ncclGetErrorString"));
-		api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.GetErrorString;
+		api.AllGather = reinterpret_cast<decltype(api.AllGather)>(dlsym(api.handle, "ncclAllGather"));
+		api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.AllGather && api.GetErrorString;
 	});
 	return api;
 }
@@ -229,6 +231,17 @@ struct trlda_model {
 	// multi-GPU
 	ncclComm_t comm = nullptr;
 	int rank = 0, nranks = 1;
+	// peer-mapped replicas (cudaIpc) for the fused reduce-scatter + M-step + all-gather kernel: [rank] pointers to
+	// every rank's sstats, beta and the two lambda buffers; peer_ready once the handles have been exchanged
+	DevBuf sstats32;                           // float32 partial statistics for the peer exchange in mixed mode
+	int peer_sstats_elem = 8;
+	bool lambda_sharded = false;               // debug: the last M-step left lambda complete only on the owners' shards
+	bool peer_ready = false;
+	bool use_peer = true;                      // TRLDA_MULTI_GPU=allreduce selects the plain NCCL all-reduce path
+	void* peer_sstats[TRLDA_MAX_RANKS] = {};
+	void* peer_beta[TRLDA_MAX_RANKS] = {};
+	void* peer_lam[2][TRLDA_MAX_RANKS] = {};
+	std::vector<void*> peer_opened;
 
 	// instrumentation
 	bool profiling = false;
@@ -707,8 +720,10 @@ int reduce_doc_stat(trlda_model* m) {
 }
 
 // dense sufficient statistics of the last E-step (summed over ranks) -> sstats   (lda.cpp:207-217)
-int run_scatter_dense(trlda_model* m) {
-	CUDA_TRY(m, m->sstats.ensure(kv_bytes(m)));
+int run_scatter_dense(trlda_model* m, bool reduce_over_ranks = true, bool for_peers = false) {
+	const bool as_float = for_peers && m->peer_sstats_elem == 4;
+	if(!as_float)
+		CUDA_TRY(m, m->sstats.ensure(kv_bytes(m)));
 	ScatterArgs a;
 	a.K = m->K;
 	a.V = m->V;
@@ -718,20 +733,30 @@ int run_scatter_dense(trlda_model* m) {
 	a.beta = m->beta.p;
 	a.beta_elem = m->beta_elem;
 	a.sstats = m->sstats.as<double>();
+	a.sstats32 = as_float ? m->sstats32.as<float>() : nullptr;
 	a.fused = false;
 	{
 		Launch l(m, KK_SCATTER);
 		launch_scatter(a, m->docs, m->stream);
 	}
 	TRY(check_launch(m, "scatter"));
+	if(!reduce_over_ranks)
+		return TRLDA_OK;
 	return allreduce(m, m->sstats.p, (size_t) m->K * m->V, ncclDouble);
+}
+
+// all ranks have finished the work enqueued before this point (a one-element all-reduce on the model's stream)
+int rank_barrier(trlda_model* m) {
+	if(m->nranks <= 1)
+		return TRLDA_OK;
+	return allreduce(m, m->scalars.as<double>() + 4000, 1, ncclDouble);
 }
 
 // M-step: rebuild lambda from the last E-step.  lambda' is the CURRENT buffer unless `prime` is given; the new
 // lambda goes to the other buffer and becomes current.  Also refreshes rows / psi_rows (by linearity of the
 // blend) and, if asked, beta and the per-word psi sums for the eta update.
 int run_mstep(trlda_model* m, const MStepCoef& coef, const double* prime, double* target, bool write_beta,
-              bool want_psi_partials, bool force_dense) {
+              bool want_psi_partials, bool force_dense, bool broadcast_lambda = true) {
 	TRY(reduce_doc_stat(m));
 	double a = 0, b = 0, c = 0;
 	if(coef.mode == MSTEP_ONLINE) {
@@ -751,6 +776,47 @@ int run_mstep(trlda_model* m, const MStepCoef& coef, const double* prime, double
 		Launch l(m, KK_MISC);
 		launch_rows_update(coef.mode == MSTEP_BATCH ? nullptr : m->rows_prev.as<double>(), m->rows_stat.as<double>(), a, b, c,
 		                   m->K, m->rows.as<double>(), m->psi_rows.as<double>(), m->stream);
+	}
+	if(m->nranks > 1 && m->peer_ready && m->use_peer && !force_dense && m->K % 4 == 0) {
+		// fused path over NVLink peer memory: local scatter, barrier, then one kernel per rank that pulls every
+		// rank's partial statistics for its word shard, blends, and pushes beta (and lambda when the caller needs
+		// the full matrix afterwards) into every replica
+		TRY(run_scatter_dense(m, false, true));
+		TRY(rank_barrier(m));
+		const int target_index = target == m->lam[0].as<double>() ? 0 : 1;
+		ShardMStepArgs sa;
+		sa.K = m->K;
+		sa.V = m->V;
+		sa.v0 = (int) ((int64_t) m->V * m->rank / m->nranks);
+		sa.v1 = (int) ((int64_t) m->V * (m->rank + 1) / m->nranks);
+		sa.nranks = m->nranks;
+		sa.rank = m->rank;
+		sa.coef = coef;
+		for(int r = 0; r < m->nranks; ++r) {
+			sa.sstats[r] = m->peer_sstats[r];
+			sa.beta[r] = m->peer_beta[r];
+			sa.lambda[r] = static_cast<double*>(m->peer_lam[target_index][r]);
+		}
+		sa.sstats_elem = m->peer_sstats_elem;
+		sa.lambda_prime = prime;
+		sa.psi_rows = m->psi_rows.as<double>();
+		sa.beta_elem = m->beta_elem;
+		sa.write_beta = write_beta;
+		sa.broadcast_lambda = broadcast_lambda;
+		sa.psi_partials = want_psi_partials ? m->vpartials.as<double>() : nullptr;
+		if(want_psi_partials)
+			CUDA_TRY(m, cudaMemsetAsync(m->vpartials.p, 0, sizeof(double) * m->V, m->stream));
+		{
+			Launch l(m, KK_MSTEP);
+			launch_mstep_shard(sa, m->stream);
+		}
+		TRY(check_launch(m, "mstep_shard"));
+		TRY(rank_barrier(m));
+		if(want_psi_partials)
+			TRY(allreduce(m, m->vpartials.p, m->V, ncclDouble));
+		m->beta_valid = write_beta;
+		m->lambda_sharded = !broadcast_lambda;
+		return TRLDA_OK;
 	}
 	const bool dense = force_dense || m->nranks > 1;
 	if(dense) {
@@ -974,7 +1040,7 @@ int online_update(trlda_model* m, const trlda_params* p, double* result) {
 				const bool last = i == p->max_iter_tr - 1;
 				TRY(run_estep(m, (i > 0 && p->init_gamma) ? GAMMA_KEEP : GAMMA_FRESH, nullptr, p->max_iter_inference, p->threshold));
 				const bool dense = last && p->adaptive;
-				TRY(run_mstep(m, coef, prime, target, !last, last && p->update_eta, dense));
+				TRY(run_mstep(m, coef, prime, target, !last, last && p->update_eta, dense, last));
 				have_psi_partials = last && p->update_eta;
 				have_dense_sstats = dense || m->nranks > 1;
 			}
@@ -1066,7 +1132,7 @@ int batch_update(trlda_model* m, const trlda_params* p, double* result) {
 			TRY(prepare_beta(m));
 			TRY(run_estep(m, GAMMA_FRESH, nullptr, p->max_iter_inference, p->threshold));
 			MStepCoef coef{MSTEP_BATCH, 1., m->eta, 1.};
-			TRY(run_mstep(m, coef, nullptr, m->lambda_next(), true, p->update_eta, false));
+			TRY(run_mstep(m, coef, nullptr, m->lambda_next(), true, p->update_eta, false, epoch == p->max_epochs - 1));
 			m->cur = 1 - m->cur;
 			have_psi_partials = p->update_eta;
 		}
@@ -1153,7 +1219,7 @@ int cumulative_update(trlda_model* m, const trlda_params* p, double* result) {
 			TRY(prepare_beta(m));
 			TRY(run_estep(m, GAMMA_FRESH, nullptr, p->max_iter_inference, p->threshold));
 			MStepCoef coef{MSTEP_CUMULATIVE, 1., m->eta, 1.};
-			TRY(run_mstep(m, coef, prime, work, true, false, false));
+			TRY(run_mstep(m, coef, prime, work, true, false, false, epoch == p->max_epochs - 1));
 		}
 	}
 
@@ -1366,12 +1432,14 @@ void trlda_destroy(trlda_model* m) {
 			fprintf(stderr, "[trlda]   %-26s %10.0f cycles/doc\n", names[i], t[15] ? (double) t[i] / (double) t[15] : 0.0);
 		m->ticks.release();
 	}
+	for(void* p : m->peer_opened)
+		cudaIpcCloseMemHandle(p);
 	if(m->comm && nccl_api().ok)
 		nccl_api().CommDestroy(m->comm);
 	collect_spans(m);
 	for(cudaEvent_t e : m->event_pool)
 		cudaEventDestroy(e);
-	DevBuf* bufs[] = {&m->ada_gradient, &m->lam[0], &m->lam[1], &m->beta, &m->sstats, &m->rows, &m->rows_prev, &m->rows_stat,
+	DevBuf* bufs[] = {&m->ada_gradient, &m->lam[0], &m->lam[1], &m->beta, &m->sstats, &m->sstats32, &m->rows, &m->rows_prev, &m->rows_stat,
 	                  &m->psi_rows, &m->d_alpha, &m->partials, &m->vpartials, &m->scalars, &m->b_doc_ptr, &m->b_word_ids,
 	                  &m->b_counts, &m->b_word_ptr, &m->b_tok_doc, &m->b_tok_src, &m->b_order, &m->wordcount, &m->gamma, &m->etheta,
 	                  &m->etheta32, &m->weight, &m->doc_stat, &m->iterations};
@@ -1402,6 +1470,7 @@ int trlda_set_precision(trlda_model* m, int precision) {
 		m->precision = precision;
 		m->beta_valid = false;
 		m->beta.release();
+		m->peer_ready = false;   // the peer-mapped beta replicas are gone: fall back to the all-reduce exchange
 	}
 	return TRLDA_OK;
 }
@@ -1630,6 +1699,66 @@ int trlda_comm_init(trlda_model* m, const void* id_bytes, int rank, int nranks) 
 	NCCL_TRY(m, nccl_api().CommInitRank(&m->comm, nranks, id, rank));
 	m->rank = rank;
 	m->nranks = nranks;
+	if(const char* mode = getenv("TRLDA_MULTI_GPU"))
+		m->use_peer = strcmp(mode, "allreduce") != 0;
+	if(!m->use_peer || nranks > TRLDA_MAX_RANKS)
+		return TRLDA_OK;
+
+	// Map every rank's sstats / beta / lambda buffers into this process (cudaIpc over NVLink) for the fused
+	// reduce-scatter + M-step + all-gather kernel.  The four handles travel through the communicator itself.
+	TRY(ensure_beta(m));
+	TRY(ensure_small(m));
+	CUDA_TRY(m, m->lam[1 - m->cur].ensure(kv_bytes(m)));
+	// mixed mode exchanges the per-rank partial statistics rounded to float32 (they are summed in float64)
+	m->peer_sstats_elem = (m->beta_elem == 4 && m->K % 4 == 0) ? 4 : 8;
+	if(m->peer_sstats_elem == 4)
+		CUDA_TRY(m, m->sstats32.ensure(kv_bytes(m) / 2));
+	else
+		CUDA_TRY(m, m->sstats.ensure(kv_bytes(m)));
+	void* mine[4] = {m->peer_sstats_elem == 4 ? m->sstats32.p : m->sstats.p, m->beta.p, m->lam[0].p, m->lam[1].p};
+	std::vector<cudaIpcMemHandle_t> handles((size_t) 4 * nranks);
+	cudaIpcMemHandle_t local[4];
+	for(int i = 0; i < 4; ++i)
+		CUDA_TRY(m, cudaIpcGetMemHandle(&local[i], mine[i]));
+	DevBuf send, recv;
+	CUDA_TRY(m, send.ensure(sizeof(local)));
+	CUDA_TRY(m, recv.ensure(sizeof(local) * nranks));
+	CUDA_TRY(m, cudaMemcpyAsync(send.p, local, sizeof(local), cudaMemcpyHostToDevice, m->stream));
+	NCCL_TRY(m, nccl_api().AllGather(send.p, recv.p, sizeof(local), ncclUint8, m->comm, m->stream));
+	CUDA_TRY(m, cudaMemcpyAsync(handles.data(), recv.p, sizeof(local) * nranks, cudaMemcpyDeviceToHost, m->stream));
+	CUDA_TRY(m, cudaStreamSynchronize(m->stream));
+	send.release();
+	recv.release();
+	bool ok = true;
+	for(int r = 0; r < nranks && ok; ++r) {
+		void* ptrs[4];
+		for(int i = 0; i < 4; ++i) {
+			if(r == rank) {
+				ptrs[i] = mine[i];
+			} else if(cudaIpcOpenMemHandle(&ptrs[i], handles[(size_t) 4 * r + i], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess) {
+				m->peer_opened.push_back(ptrs[i]);
+			} else {
+				cudaGetLastError();
+				ok = false;
+				break;
+			}
+		}
+		if(ok) {
+			m->peer_sstats[r] = ptrs[0];
+			m->peer_beta[r] = ptrs[1];
+			m->peer_lam[0][r] = ptrs[2];
+			m->peer_lam[1][r] = ptrs[3];
+		}
+	}
+	// every rank must take the same path: agree on success
+	double* flag = m->scalars.as<double>() + 4001;
+	const double mine_ok = ok ? 0.0 : 1.0;
+	CUDA_TRY(m, cudaMemcpyAsync(flag, &mine_ok, sizeof(double), cudaMemcpyHostToDevice, m->stream));
+	TRY(allreduce(m, flag, 1, ncclDouble));
+	double failures = 0.0;
+	CUDA_TRY(m, cudaMemcpyAsync(&failures, flag, sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+	CUDA_TRY(m, cudaStreamSynchronize(m->stream));
+	m->peer_ready = failures == 0.0;
 	return TRLDA_OK;
 }
 
