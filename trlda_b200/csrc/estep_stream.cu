@@ -165,7 +165,7 @@ k_estep_stream(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, 
 			__syncwarp();
 			const T* col = my_ring + (size_t) stage * KP;
 			T c[NVEC][VN];
-			T part = T(0);
+			double part = 0.0;
 			#pragma unroll
 			for(int v = 0; v < NVEC; ++v) {
 				const int row = (v * 32 + lane) * VN;
@@ -176,11 +176,14 @@ k_estep_stream(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, 
 					for(int q = 0; q < VN; ++q)
 						c[v][q] = T(0);
 				}
+				// products of one 16-byte chunk are summed in T, chunks are added in float64
+				T chunk = e[v][0] * c[v][0];
 				#pragma unroll
-				for(int q = 0; q < VN; ++q)
-					part = fma(e[v][q], c[v][q], part);
+				for(int q = 1; q < VN; ++q)
+					chunk = fma(e[v][q], c[v][q], chunk);
+				part += (double) chunk;
 			}
-			const double phi = warp_sum((double) part) + 1e-100;          // lda.cpp:183,199
+			const double phi = warp_sum(part) + 1e-100;                    // lda.cpp:183,199
 			const double w = (double) cnt[j] / phi;                        // lda.cpp:192
 			const T wt = (T) w;
 			#pragma unroll

@@ -934,18 +934,18 @@ void launch_mstep_shard(const ShardMStepArgs& a, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------------------
 // phi = 1/K warm start (onlinelda.cpp:79-86) + beta-prep
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_wordcount(DeviceDocs docs, int V, double* __restrict__ wordcount) {
-	const int w = blockIdx.x * blockDim.x + threadIdx.x;
-	if(w >= V)
-		return;
-	double c = 0.0;
-	for(int t = docs.word_ptr[w]; t < docs.word_ptr[w + 1]; ++t)
-		c += docs.counts[docs.tok_src[t]];
-	wordcount[w] = c;
+// wordcount[w] = sum of the counts of word w over the minibatch (onlinelda.cpp:79-82).  Atomic adds of integers
+// held in doubles are exact, hence order-independent: the result is deterministic and needs no word-sorted list.
+__global__ void __launch_bounds__(256) k_wordcount(DeviceDocs docs, double* __restrict__ wordcount) {
+	const int64_t t = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	if(t < docs.N)
+		atomicAdd(wordcount + docs.word_ids[t], (double) docs.counts[t]);
 }
 
 void launch_wordcount(const DeviceDocs& docs, int V, double* wordcount, cudaStream_t s) {
-	k_wordcount<<<ceil_div(V, 256), 256, 0, s>>>(docs, V, wordcount);
+	cudaMemsetAsync(wordcount, 0, sizeof(double) * V, s);
+	if(docs.N > 0)
+		k_wordcount<<<(unsigned) ((docs.N + 255) / 256), 256, 0, s>>>(docs, wordcount);
 }
 
 template <typename TB>

@@ -206,6 +206,10 @@ struct trlda_model {
 	struct Bucket { int64_t offset, count; int n_max; };
 	std::vector<Bucket> buckets;
 	bool force_generic = false;
+	// the word-sorted token list of the resident minibatch is built lazily (ensure_csc)
+	bool csc_pending = false;
+	int csc_threads = 1;
+	size_t stage_off[5] = {0, 0, 0, 0, 0};
 	// the length buckets of one E-step run concurrently on these streams (fork/join around the main stream), so
 	// that CTAs of buckets with different shared-memory footprints can share an SM and the buckets' tails overlap
 	static const int kAuxStreams = 3;
@@ -456,68 +460,44 @@ int upload_docs(trlda_model* m, const trlda_docs* docs) {
 			return fail(m, TRLDA_ERR_ARG, "Document offsets must be non-decreasing.");
 		n_max = std::max<int64_t>(n_max, n);
 	}
-	// stable counting sort of the tokens by word id, parallel over word ranges: thread t owns the words
-	// [V t / T, V (t+1) / T), scans the whole token stream in order and handles only its own words, so the
-	// order of a word's tokens (document order) does not depend on the number of threads
+	// copy the id / count arrays into the pinned staging buffer (parallel slices), summing the counts and checking
+	// the id range on the way.  The word-sorted token list is built later, by ensure_csc(), right before the
+	// first kernel that needs it — by then the device is busy with the first E-step and the host work is hidden.
+	const int T = (int) std::max(1u, std::min(8u, std::min(std::thread::hardware_concurrency(), (unsigned) (N / 65536 + 1))));
 	{
-		const int T = (int) std::max(1u, std::min(8u, std::min(std::thread::hardware_concurrency(), (unsigned) (N / 65536 + 1))));
-		std::vector<int64_t> owned(T, 0), counts_sum(T, 0);
-		memset(s_wptr, 0, sizeof(int32_t) * ((size_t) V + 1));
+		std::vector<int64_t> counts_sum(T, 0);
+		std::vector<int> bad(T, 0);
 		const int32_t* ids = docs->word_ids;
 		const int32_t* cts = docs->counts;
-		auto range_of = [&](int t) { return std::make_pair((int32_t) ((int64_t) V * t / T), (int32_t) ((int64_t) V * (t + 1) / T)); };
-		auto run = [&](auto&& fn) {
-			std::vector<std::thread> pool;
-			for(int t = 1; t < T; ++t)
-				pool.emplace_back(fn, t);
-			fn(0);
-			for(auto& th : pool)
-				th.join();
-		};
-		run([&](int t) {
-			const auto r = range_of(t);
-			int64_t mine = 0, csum = 0;
-			// thread t also copies its slice of the id / count arrays into the pinned staging buffer
+		auto body = [&](int t) {
 			const int64_t c0 = N * t / T, c1 = N * (t + 1) / T;
-			if(c1 > c0) {
-				memcpy(s_ids + c0, ids + c0, sizeof(int32_t) * (c1 - c0));
-				memcpy(s_cts + c0, cts + c0, sizeof(int32_t) * (c1 - c0));
-				for(int64_t i = c0; i < c1; ++i)
-					csum += cts[i];
+			if(c1 <= c0)
+				return;
+			memcpy(s_ids + c0, ids + c0, sizeof(int32_t) * (c1 - c0));
+			memcpy(s_cts + c0, cts + c0, sizeof(int32_t) * (c1 - c0));
+			int64_t csum = 0;
+			int oob = 0;
+			for(int64_t i = c0; i < c1; ++i) {
+				csum += cts[i];
+				oob |= (ids[i] < 0) | (ids[i] >= V);
 			}
-			for(int64_t i = 0; i < N; ++i) {
-				const int32_t w = ids[i];
-				if(w >= r.first && w < r.second) {
-					s_wptr[w + 1]++;
-					++mine;
-				}
-			}
-			owned[t] = mine;
 			counts_sum[t] = csum;
-		});
-		int64_t seen = 0;
+			bad[t] = oob;
+		};
+		std::vector<std::thread> pool;
+		for(int t = 1; t < T; ++t)
+			pool.emplace_back(body, t);
+		body(0);
+		for(auto& th : pool)
+			th.join();
 		for(int t = 0; t < T; ++t) {
-			seen += owned[t];
 			total_count += counts_sum[t];
+			if(bad[t])
+				return fail(m, TRLDA_ERR_ARG, "Word ID out of range.");
 		}
-		if(seen != N)
-			return fail(m, TRLDA_ERR_ARG, "Word ID out of range.");
-		for(int w = 0; w < V; ++w)
-			s_wptr[w + 1] += s_wptr[w];
-		std::vector<int32_t> cursor(s_wptr, s_wptr + V);
-		run([&](int t) {
-			const auto r = range_of(t);
-			for(int64_t d = 0; d < B; ++d)
-				for(int64_t i = s_ptr[d]; i < s_ptr[d + 1]; ++i) {
-					const int32_t w = ids[i];
-					if(w >= r.first && w < r.second) {
-						const int32_t pos = cursor[w]++;
-						s_tdoc[pos] = (int32_t) d;
-						s_tsrc[pos] = (int32_t) i;
-					}
-				}
-		});
 	}
+	m->csc_pending = true;
+	m->csc_threads = T;
 
 	// length buckets for the E-step: counting sort by length, longest first
 	m->buckets.clear();
@@ -561,10 +541,9 @@ int upload_docs(trlda_model* m, const trlda_docs* docs) {
 	if(N) {
 		CUDA_TRY(m, cudaMemcpyAsync(m->b_word_ids.p, s_ids, sizeof(int32_t) * N, cudaMemcpyHostToDevice, m->stream));
 		CUDA_TRY(m, cudaMemcpyAsync(m->b_counts.p, s_cts, sizeof(int32_t) * N, cudaMemcpyHostToDevice, m->stream));
-		CUDA_TRY(m, cudaMemcpyAsync(m->b_tok_doc.p, s_tdoc, sizeof(int32_t) * N, cudaMemcpyHostToDevice, m->stream));
-		CUDA_TRY(m, cudaMemcpyAsync(m->b_tok_src.p, s_tsrc, sizeof(int32_t) * N, cudaMemcpyHostToDevice, m->stream));
 	}
-	CUDA_TRY(m, cudaMemcpyAsync(m->b_word_ptr.p, s_wptr, sizeof(int32_t) * ((size_t) V + 1), cudaMemcpyHostToDevice, m->stream));
+	(void) s_wptr; (void) s_tdoc; (void) s_tsrc;
+	m->stage_off[0] = o_ptr; m->stage_off[1] = o_ids; m->stage_off[2] = o_wptr; m->stage_off[3] = o_tdoc; m->stage_off[4] = o_tsrc;
 	if(B)
 		CUDA_TRY(m, cudaMemcpyAsync(m->b_order.p, s_order, sizeof(int32_t) * B, cudaMemcpyHostToDevice, m->stream));
 	m->stats.h2d_bytes += total;
@@ -719,8 +698,66 @@ int reduce_doc_stat(trlda_model* m) {
 	return allreduce(m, m->rows_stat.p, m->K, ncclDouble);
 }
 
+// Builds the word-sorted token list (CSC view) of the resident minibatch from the pinned staging copy and sends it
+// to the device.  Stable counting sort, parallel over word ranges: thread t owns the words [V t / T, V (t+1) / T),
+// scans the whole token stream in order and places only its own words, so a word's tokens stay in document order
+// whatever the number of threads.
+int ensure_csc(trlda_model* m) {
+	if(!m->csc_pending)
+		return TRLDA_OK;
+	m->csc_pending = false;
+	const int64_t B = m->docs.B, N = m->docs.N;
+	const int V = m->V, T = m->csc_threads;
+	char* base = m->staging.as<char>();
+	const int64_t* s_ptr = reinterpret_cast<const int64_t*>(base + m->stage_off[0]);
+	const int32_t* ids = reinterpret_cast<const int32_t*>(base + m->stage_off[1]);
+	int32_t* s_wptr = reinterpret_cast<int32_t*>(base + m->stage_off[2]);
+	int32_t* s_tdoc = reinterpret_cast<int32_t*>(base + m->stage_off[3]);
+	int32_t* s_tsrc = reinterpret_cast<int32_t*>(base + m->stage_off[4]);
+	memset(s_wptr, 0, sizeof(int32_t) * ((size_t) V + 1));
+	auto range_of = [&](int t) { return std::make_pair((int32_t) ((int64_t) V * t / T), (int32_t) ((int64_t) V * (t + 1) / T)); };
+	auto run = [&](auto&& fn) {
+		std::vector<std::thread> pool;
+		for(int t = 1; t < T; ++t)
+			pool.emplace_back(fn, t);
+		fn(0);
+		for(auto& th : pool)
+			th.join();
+	};
+	run([&](int t) {
+		const auto r = range_of(t);
+		for(int64_t i = 0; i < N; ++i) {
+			const int32_t w = ids[i];
+			if(w >= r.first && w < r.second)
+				s_wptr[w + 1]++;
+		}
+	});
+	for(int w = 0; w < V; ++w)
+		s_wptr[w + 1] += s_wptr[w];
+	std::vector<int32_t> cursor(s_wptr, s_wptr + V);
+	run([&](int t) {
+		const auto r = range_of(t);
+		for(int64_t d = 0; d < B; ++d)
+			for(int64_t i = s_ptr[d]; i < s_ptr[d + 1]; ++i) {
+				const int32_t w = ids[i];
+				if(w >= r.first && w < r.second) {
+					const int32_t pos = cursor[w]++;
+					s_tdoc[pos] = (int32_t) d;
+					s_tsrc[pos] = (int32_t) i;
+				}
+			}
+	});
+	if(N) {
+		CUDA_TRY(m, cudaMemcpyAsync(m->b_tok_doc.p, s_tdoc, sizeof(int32_t) * N, cudaMemcpyHostToDevice, m->stream));
+		CUDA_TRY(m, cudaMemcpyAsync(m->b_tok_src.p, s_tsrc, sizeof(int32_t) * N, cudaMemcpyHostToDevice, m->stream));
+	}
+	CUDA_TRY(m, cudaMemcpyAsync(m->b_word_ptr.p, s_wptr, sizeof(int32_t) * ((size_t) V + 1), cudaMemcpyHostToDevice, m->stream));
+	return TRLDA_OK;
+}
+
 // dense sufficient statistics of the last E-step (summed over ranks) -> sstats   (lda.cpp:207-217)
 int run_scatter_dense(trlda_model* m, bool reduce_over_ranks = true, bool for_peers = false) {
+	TRY(ensure_csc(m));
 	const bool as_float = for_peers && m->peer_sstats_elem == 4;
 	if(!as_float)
 		CUDA_TRY(m, m->sstats.ensure(kv_bytes(m)));
@@ -836,6 +873,7 @@ int run_mstep(trlda_model* m, const MStepCoef& coef, const double* prime, double
 		Launch l(m, KK_MSTEP);
 		launch_mstep(ma, m->stream);
 	} else {
+		TRY(ensure_csc(m));
 		ScatterArgs sa;
 		sa.K = m->K;
 		sa.V = m->V;
