@@ -139,13 +139,13 @@ _CPU_MODEL = {}
 
 
 def cpu_model(w):
-	"""The CPU implementation, constructed once per process: the reference's constructor draws lambda with
-	100 K V calls to rand() (lda.cpp:71 -> utils.cpp:224-231), about two minutes at cfg-3, before we overwrite it."""
+	"""The CPU implementation, constructed once per process."""
 	key = (w['V'], w['K'])
 	if key not in _CPU_MODEL:
 		from oracle import pyoracle
 		if pyoracle.have_ref():
-			_CPU_MODEL[key] = (pyoracle, pyoracle.RefModel('online', w['V'], w['K'], w['D'], w['alpha'], w['eta']), 'reference')
+			# fast_init: skip the constructor's rand() draw of lambda (minutes at cfg-3); lambda0 is installed before every timed call
+			_CPU_MODEL[key] = (pyoracle, pyoracle.RefModel('online', w['V'], w['K'], w['D'], w['alpha'], w['eta'], fast_init=True), 'reference')
 		else:
 			if not pyoracle.have_port():
 				pyoracle.build(ref=False)

@@ -154,6 +154,8 @@ def ref_lib():
 	lib = _load(REF_SO)
 	lib.ref_create.restype = C.c_void_p
 	lib.ref_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.c_double]
+	lib.ref_create_fast.restype = C.c_void_p
+	lib.ref_create_fast.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.c_double]
 	lib.ref_destroy.argtypes = [C.c_void_p]
 	lib.ref_last_error.restype = C.c_char_p
 	lib.ref_last_error.argtypes = [C.c_void_p]
@@ -237,12 +239,15 @@ class RefModel(object):
 
 	backend = 'reference'
 
-	def __init__(self, kind, num_words, num_topics, num_documents=0, alpha=.1, eta=.3, seed=0):
+	def __init__(self, kind, num_words, num_topics, num_documents=0, alpha=.1, eta=.3, seed=0, fast_init=False):
+		"""fast_init: lambda starts as eta everywhere instead of the constructor's Gamma(100, 1/100) draw, which
+		costs 100 K V calls to rand() (minutes at K V = 1e8); for callers that install their own lambda next."""
 		self.lib = ref_lib()
 		self.kind, self.V, self.K = kind, num_words, num_topics
 		a = _alpha_vector(alpha, num_topics)
 		self.lib.ref_srand(seed)
-		self.h = self.lib.ref_create(KIND[kind], num_words, num_topics, num_documents, _dptr(a), eta)
+		create = self.lib.ref_create_fast if fast_init else self.lib.ref_create
+		self.h = create(KIND[kind], num_words, num_topics, num_documents, _dptr(a), eta)
 
 	def __del__(self):
 		if getattr(self, 'h', None):

@@ -35,6 +35,13 @@ struct Injected : public Base {
 
 	const ArrayXXd* injected;
 
+	// Replaces lambda (a protected member, lda.h:134) by a constant matrix of any width.  Used by ref_create_fast to
+	// skip the constructor's 100 K V calls to rand() (lda.cpp:71 -> utils.cpp:224-231: minutes at K V = 1e8) when the
+	// caller overwrites lambda anyway; the object is first constructed with numWords = 1.
+	void resetLambda(int numTopics, int numWords, double value) {
+		this->mLambda = ArrayXXd::Constant(numTopics, numWords, value);
+	}
+
 	using Base::updateVariables;
 	virtual pair<ArrayXXd, ArrayXXd> updateVariables(
 		const LDA::Documents& documents,
@@ -51,6 +58,7 @@ struct Handle {
 	LDA* lda;
 	const ArrayXXd** slot;
 	const char* error;
+	bool fast;     // built by ref_create_fast: OnlineLDA's private mAdaGradient has the wrong width, adaptive mode is off limits
 };
 
 LDA::Documents toDocuments(const trlda_docs* docs) {
@@ -80,6 +88,7 @@ void* ref_create(int kind, int numWords, int numTopics, int numDocuments, const 
 	Handle* h = new Handle();
 	h->kind = kind;
 	h->error = "";
+	h->fast = false;
 	ArrayXd a = Map<const ArrayXd>(alpha, numTopics);
 	if(kind == TRLDA_KIND_ONLINE) {
 		Injected<OnlineLDA>* m = new Injected<OnlineLDA>(numWords, numDocuments, a, eta);
@@ -89,6 +98,30 @@ void* ref_create(int kind, int numWords, int numTopics, int numDocuments, const 
 		h->lda = m; h->slot = &m->injected;
 	} else {
 		Injected<CumulativeLDA>* m = new Injected<CumulativeLDA>(numWords, a, eta);
+		h->lda = m; h->slot = &m->injected;
+	}
+	return h;
+}
+
+/* Same object as ref_create, but lambda is set to eta everywhere instead of being drawn with rand(): for callers
+ * that install their own lambda next (the benchmark), so that construction takes milliseconds instead of minutes. */
+void* ref_create_fast(int kind, int numWords, int numTopics, int numDocuments, const double* alpha, double eta) {
+	Handle* h = new Handle();
+	h->kind = kind;
+	h->error = "";
+	h->fast = true;
+	ArrayXd a = Map<const ArrayXd>(alpha, numTopics);
+	if(kind == TRLDA_KIND_ONLINE) {
+		Injected<OnlineLDA>* m = new Injected<OnlineLDA>(1, numDocuments, a, eta);
+		m->resetLambda(numTopics, numWords, eta);
+		h->lda = m; h->slot = &m->injected;
+	} else if(kind == TRLDA_KIND_BATCH) {
+		Injected<BatchLDA>* m = new Injected<BatchLDA>(1, a, eta);
+		m->resetLambda(numTopics, numWords, eta);
+		h->lda = m; h->slot = &m->injected;
+	} else {
+		Injected<CumulativeLDA>* m = new Injected<CumulativeLDA>(1, a, eta);
+		m->resetLambda(numTopics, numWords, eta);
 		h->lda = m; h->slot = &m->injected;
 	}
 	return h;
@@ -192,6 +225,10 @@ int ref_update_parameters(void* h_, const trlda_docs* docs, const trlda_params* 
                           const double* gamma0, int rows, long cols, double* result)
 {
 	Handle* h = static_cast<Handle*>(h_);
+	if(h->fast && params->adaptive) {
+		h->error = "adaptive mode needs a model built by ref_create";
+		return 1;
+	}
 	try {
 		LDA::Documents documents = toDocuments(docs);
 		LDA::Parameters parameters = toParameters(params);

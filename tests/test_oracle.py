@@ -158,3 +158,29 @@ def test_estep_edge_cases_port_vs_reference(oracle_built):
 			out.append(model.update_variables(docs, g0, max_iter=max_iter))
 		assert rel_err_elementwise(out[1][0], out[0][0]) < 1e-13
 		assert rel_err(out[1][1], out[0][1]) < 1e-13
+
+
+def test_fast_constructed_reference_is_the_same_model(oracle_built):
+	"""bench.py builds the reference with fast_init (no rand() draw of lambda in the constructor); once lambda is
+	installed it must behave exactly like a normally constructed reference"""
+	if not oracle_built.have_ref():
+		pytest.skip('compiled reference not present on this box')
+	from common import random_docs
+	rng = np.random.default_rng(2)
+	K, V, B = 7, 50, 11
+	docs = oracle_built.CSR.from_lists(random_docs(rng, B, V, 20))
+	lam0 = np.asfortranarray(rng.gamma(100., .01, size=(V, K)).T)
+	g0 = np.asfortranarray(rng.gamma(100., .01, size=(B, K)).T)
+	out = []
+	for fast in (False, True):
+		model = oracle_built.RefModel('online', V, K, 300, .1, .2, fast_init=fast)
+		assert model.lambdas.shape == (K, V)
+		if fast:
+			assert np.all(model.lambdas == .2)
+		model.lambdas = lam0
+		rho = model.update_parameters(docs, gamma0=g0, max_iter_tr=3, max_iter_inference=20, update_alpha=1, update_eta=1)
+		out.append((rho, model.lambdas, model.alpha, model.eta))
+	assert out[0][0] == out[1][0] and out[0][3] == out[1][3]
+	assert np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][2], out[1][2])
+	with pytest.raises(RuntimeError):
+		oracle_built.RefModel('online', V, K, 300, .1, .2, fast_init=True).update_parameters(docs, gamma0=g0, adaptive=1)

@@ -53,6 +53,7 @@ __host__ __device__ inline StreamSmem stream_smem_layout(int NW, int kp, int n_c
 	return L;
 }
 
+static bool g_stream_shuffle = false; // TRLDA_STREAM_SHUFFLE=1: strided document order (measured: no gain over longest-first)
 static int g_stream_warps_f32 = 8;    // TRLDA_STREAM_WARPS: 8 (two CTAs per SM, default) or 16 (one)
 static inline int stream_warps(int elem) { return elem == 4 ? g_stream_warps_f32 : 8; }
 static inline int stream_nvec(int K, int elem) {
@@ -77,7 +78,8 @@ bool stream_estep_applicable(int K, int n_max, int elem, int smem_optin) {
 
 template <typename T, int NW, int NVEC>
 __global__ void __launch_bounds__(NW * 32, (NW == 4 ? 3 : (NW == 8 && sizeof(T) == 4 ? 2 : 1)))
-k_estep_stream(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, int64_t doc_offset, int n_cap) {
+k_estep_stream(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, int64_t doc_offset, int n_cap,
+               unsigned stride, unsigned count) {
 	extern __shared__ __align__(128) unsigned char smem[];
 	using V = typename SVec<T>::type;
 	constexpr int VN = SVec<T>::N;
@@ -92,7 +94,10 @@ k_estep_stream(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, 
 	int* wid = reinterpret_cast<int*>(smem + L.wid);
 	int* cnt = reinterpret_cast<int*>(smem + L.cnt);
 
-	const int64_t slot = doc_offset + blockIdx.x;
+	// CTA i takes the (i * stride mod count)-th longest document: every wave of CTAs then holds a mix of lengths, the
+	// CTAs drift out of phase, and the HBM-bound first sweep of one document overlaps the L2-bound re-sweeps and
+	// psi phases of its neighbours instead of all CTAs hitting HBM (then L2) in lockstep
+	const int64_t slot = doc_offset + (int64_t) (((uint64_t) blockIdx.x * stride) % count);
 	const int64_t d = order ? order[slot] : slot;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int K = a.K;
@@ -259,13 +264,24 @@ template <typename T, int NW, int NVEC>
 static void launch_stream_t(const EStepArgs& args, const DeviceDocs& docs, const int32_t* order, int64_t offset,
                             int64_t count, int n_cap, size_t smem, cudaStream_t s) {
 	cudaFuncSetAttribute(k_estep_stream<T, NW, NVEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-	k_estep_stream<T, NW, NVEC><<<(unsigned) count, NW * 32, smem, s>>>(args, docs, order, offset, n_cap);
+	// a stride coprime to the document count visits every document exactly once
+	static const unsigned primes[4] = {7919u, 7907u, 7901u, 7883u};
+	unsigned stride = 1;
+	if(g_stream_shuffle && count > 1)
+		for(unsigned p : primes)
+			if(count % p != 0) {
+				stride = p;
+				break;
+			}
+	k_estep_stream<T, NW, NVEC><<<(unsigned) count, NW * 32, smem, s>>>(args, docs, order, offset, n_cap, stride, (unsigned) count);
 }
 
 void launch_estep_stream(const EStepArgs& args, const DeviceDocs& docs, const int32_t* order, int64_t offset,
                          int64_t count, int n_max, int elem_size, cudaStream_t s) {
 	if(count == 0)
 		return;
+	if(const char* e = getenv("TRLDA_STREAM_SHUFFLE"))
+		g_stream_shuffle = atoi(e) != 0;
 	if(const char* e = getenv("TRLDA_STREAM_WARPS"))
 		g_stream_warps_f32 = atoi(e) == 16 ? 16 : (atoi(e) == 4 ? 4 : 8);
 	const int nvec = stream_nvec(args.K, elem_size);
