@@ -91,18 +91,18 @@ __device__ __forceinline__ double exp_digamma(double x) {
 	return exp_digamma_shifted(x, 0.0);
 }
 
-// Same quantity for the MIXED-precision mode, where the result is rounded to float32 anyway: the recurrence stops
-// at s >= 6 (the 7-term series is then still good to ~2e-13 absolute in psi) and the one reciprocal is a float32
+// Same quantity for the MIXED-precision mode, where the result is rounded to float32 anyway: the recurrence shifts
+// to s >= 6 only (the 7-term series is then still good to ~2e-13 absolute in psi) and the one reciprocal is a float32
 // MUFU seed refined by two fp64 Newton steps (relative error ~1e-16) instead of a full fp64 division.
 __device__ __forceinline__ double exp_digamma_shifted_mixed(double x, double c) {
 	if(x <= 0.0)
 		return exp(digamma_reflect(x) - c);
+	// recurrence to s = x + 6 in closed form for x < 6 (see exp_digamma_scaled_f32), none for x >= 6
 	double num = 0.0, den = 1.0, s = x;
-	#pragma unroll 1
-	while(s < 6.0) {
-		num = fma(num, s, den);
-		den *= s;
-		s += 1.0;
+	if(x < 6.0) {
+		den = fma(fma(fma(fma(fma(x + 15.0, x, 85.0), x, 225.0), x, 274.0), x, 120.0), x, 0.0);
+		num = fma(fma(fma(fma(fma(6.0, x, 75.0), x, 340.0), x, 675.0), x, 548.0), x, 120.0);
+		s = x + 6.0;
 	}
 	const double y = s * den;
 	double q;
@@ -126,13 +126,15 @@ __device__ __forceinline__ float exp_digamma_scaled_f32(double lambda, float ek)
 	const float x = (float) lambda;
 	if(!(x > 1e-30f) || x > 1e30f)
 		return (float) (exp_digamma_shifted_mixed(lambda, 0.0) * (double) ek);
-	float num = 0.0f, den = 1.0f, s = x;
-	#pragma unroll 1
-	while(s < 6.0f) {
-		num = fmaf(num, s, den);
-		den *= s;
-		s += 1.0f;
-	}
+	// Branch-free recurrence: for x < 64 always shift by six, sum_{i<6} 1/(x+i) = D'(x)/D(x) with
+	// D(x) = x (x+1) ... (x+5) = x^6 + 15 x^5 + 85 x^4 + 225 x^3 + 274 x^2 + 120 x (all coefficients positive:
+	// Horner without cancellation); for x >= 64 no shift is needed (and D would overflow float32 much later).
+	const bool big = x >= 64.0f;
+	float den = fmaf(fmaf(fmaf(fmaf(fmaf(x + 15.0f, x, 85.0f), x, 225.0f), x, 274.0f), x, 120.0f), x, 0.0f);
+	float num = fmaf(fmaf(fmaf(fmaf(fmaf(6.0f, x, 75.0f), x, 340.0f), x, 675.0f), x, 548.0f), x, 120.0f);
+	const float s = big ? x : x + 6.0f;
+	den = big ? 1.0f : den;
+	num = big ? 0.0f : num;
 	const float q = __frcp_rn(s * den);
 	const float r = den * q;
 	const float t = fmaf(num, s, 0.5f * den) * q;
