@@ -49,6 +49,8 @@ WORKLOADS = {
 		desc='OnlineLDA K=500 V=50k batch 8192 with update_alpha, update_eta'),
 }
 CFG_INDEX = {'cfg1': 1, 'cfg3': 3, 'cfg4': 4}
+# DRAM bytes of one launch of the dominant kernel, from the committed `ncu --set full` capture (profiles/)
+NCU_TRAFFIC = {('cfg3', 'mixed'): 5.33e9}
 
 
 def parse_args():
@@ -333,8 +335,9 @@ def main():
 	achieved = est_bytes / (est_ms * 1e-3) / 1e9 if est_ms > 0 else 0.
 	kernel_ms = {k: v / args.steps for k, v in stats['ms'].items() if v > 0}
 	roofline = {
-		'kernel': 'k_estep (per-document gamma/phi fixed point)', 'bound': 'hbm', 'achieved': achieved, 'peak': peak,
-		'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None, 'peak_source': peak_source,
+		'kernel': 'k_estep_stream (per-document gamma/phi fixed point, one launch per E-step)', 'bound': 'hbm', 'achieved': achieved, 'peak': peak,
+		'unit': 'GB/s', 'frac': achieved / peak, 'traffic': NCU_TRAFFIC.get((args.workload, args.precision)), 'peak_source': peak_source,
+		'traffic_source': 'profiles/round1_ncu_full_estep_stream_scatter.csv (dram__bytes_read.sum + dram__bytes_write.sum of one warm k_estep_stream launch)',
 		'algorithmic_bytes_per_estep': est_bytes, 'avg_estep_ms': est_ms, 'launches_per_estep': est_launches / est_calls,
 		'avg_inner_iterations_last_estep': (stats['estep_doc_iterations'] / max(stats['estep_docs'], 1)),
 		'kernel_ms_per_step': kernel_ms}
@@ -346,7 +349,7 @@ def main():
 		'data': 'synthetic',
 		'config': {
 			'workload': w['desc'], 'global_batch': global_batch, 'docs_per_gpu': B, 'pairs_per_gpu': N,
-			'precision': args.precision, 'parallelism': 'docs sharded over %d GPU(s), all-reduce of sstats per TR iteration' % world,
+			'precision': args.precision, 'parallelism': ('single GPU' if world == 1 else 'docs sharded over %d GPUs; per TR iteration one fused reduce-scatter + M-step + all-gather of beta over NVLink peer memory' % world),
 			'l2': 'no flush needed: every step streams lambda/beta (%.1f GB working set >> 126 MB L2)' % (
 				K * V * (16 + s_bytes) / 1e9)},
 		'clocks': clocks,

@@ -295,3 +295,52 @@ def test_accessors_and_error_messages(capi):
 	assert np.array_equal(model.lambdas, lam) and model.lambdas.flags.f_contiguous
 	model.alpha = 2.5                                                # scalar form, lda.h:146
 	assert np.all(model.alpha == 2.5)
+
+
+# ---- full BASELINE size: properties that need no oracle --------------------------------------------------------------
+def test_full_size_cfg3_properties(capi):
+	"""cfg-3 at full size (K=1000, V=100k, B=8192, T=10, I=20), where the CPU oracle would need minutes per E-step:
+	checks size-independent identities of the algorithm instead.
+	  * E-step: phi is normalised, so every gamma column sums to sum(alpha) + the document's token count and the
+	    sufficient statistics sum to the token mass of the minibatch; row sums of sstats equal those of the
+	    per-document statistics;
+	  * M-step: the blend is linear in the row sums (onlinelda.cpp:99-100);
+	  * both precisions agree, runs are bitwise reproducible, the resident and host-buffer paths agree."""
+	from trlda_b200.synth import gamma_matrix, make_corpus
+	K, V, B, D = 1000, 100000, 8192, 1000000
+	ptr, ids, cts = make_corpus(B, V, K, .1, .2, seed=1003)
+	docs = capi.CSR(ptr, ids, cts)
+	lam0, g0 = gamma_matrix(K, V, 2003), gamma_matrix(K, B, 3003)
+	tokens = np.add.reduceat(cts, ptr[:-1]).astype(np.float64)
+
+	gammas, lams = {}, {}
+	for precision in ('fp64', 'mixed'):
+		model = capi.Model('online', V, K, D, .1, .2, precision=precision)
+		model.lambdas = lam0
+		gamma, sstats = model.update_variables(docs, g0, max_iter=20)
+		rel = 1e-12 if precision == 'fp64' else 2e-6
+		assert np.max(np.abs(gamma.sum(0) - (K * .1 + tokens)) / tokens) < rel
+		assert abs(sstats.sum() - cts.sum()) / cts.sum() < rel
+		assert np.all(sstats >= 0) and np.all(np.isfinite(gamma))
+		gammas[precision] = gamma
+
+		rows0 = lam0.sum(1)
+		rho = model.update_parameters(docs, gamma0=g0, max_iter_tr=10, max_iter_inference=20, kappa=.7, tau=100.)
+		lam1 = model.lambdas
+		assert rho == pytest.approx(100. ** -.7)
+		# sum over topics of the row sums: (1-rho) sum(lambda') + rho (K V eta + D/B * token mass)
+		want_total = (1 - rho) * rows0.sum() + rho * (K * V * .2 + D / B * cts.sum())
+		assert abs(lam1.sum() - want_total) / want_total < (1e-12 if precision == 'fp64' else 1e-6)
+		assert np.all(lam1 > 0)
+		lams[precision] = lam1
+
+		again = capi.Model('online', V, K, D, .1, .2, precision=precision)
+		again.lambdas = lam0
+		again.upload_docs(docs)
+		again.update_parameters_resident(gamma0=g0, max_iter_tr=10, max_iter_inference=20, kappa=.7, tau=100.)
+		assert np.array_equal(again.lambdas, lam1)                  # bitwise: deterministic, resident == host path
+		again.close()
+		model.close()
+
+	assert rel_err_columns(gammas['mixed'], gammas['fp64']) < TOL_MIXED
+	assert rel_err(lams['mixed'], lams['fp64']) < TOL_MIXED
