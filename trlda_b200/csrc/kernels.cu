@@ -519,6 +519,19 @@ __device__ __forceinline__ double mstep_value(const MStepCoef& c, double lambda_
 	return lambda_prime + s;                                           // cumulativelda.cpp:69
 }
 
+// multi-GPU push target of word w: (owner rank, element offset of the column inside the owner's receive buffer)
+__device__ __forceinline__ void* peer_column(const ScatterArgs& a, int w, int64_t* offset) {
+	const int G = a.peer_ranks;
+	int o = (int) ((int64_t) w * G / a.V);
+	while(o > 0 && w < (int) ((int64_t) a.V * o / G))
+		--o;
+	while(o + 1 < G && w >= (int) ((int64_t) a.V * (o + 1) / G))
+		++o;
+	const int v0 = (int) ((int64_t) a.V * o / G);
+	*offset = ((int64_t) a.peer_rank * a.peer_shard_cap + (w - v0)) * a.K;
+	return a.peer_out[o];
+}
+
 template <typename TE, typename TB, int KPT>
 __global__ void __launch_bounds__(SCATTER_THREADS, (KPT <= 8 ? 7 : 1)) k_scatter(ScatterArgs a, DeviceDocs docs) {
 	__shared__ double scratch[32];
@@ -592,7 +605,14 @@ __global__ void __launch_bounds__(SCATTER_THREADS, (KPT <= 8 ? 7 : 1)) k_scatter
 			const int64_t e = (int64_t) w * K + k;
 			const double s = acc[i] * (double) bcol[i];                  // lda.cpp:217
 			if(!a.fused) {
-				a.sstats[e] = s;
+				if(a.peer_ranks > 0) {
+					int64_t off;
+					void* dst = peer_column(a, w, &off);
+					if(a.peer_elem == 4) static_cast<float*>(dst)[off + k] = (float) s;
+					else static_cast<double*>(dst)[off + k] = s;
+				} else {
+					a.sstats[e] = s;
+				}
 				continue;
 			}
 			const double lam = mstep_value(a.coef, lp[i], s);
@@ -719,7 +739,17 @@ __global__ void __launch_bounds__(NT, (NT == 128 && NCH <= 2 ? 5 : 1)) k_scatter
 				lam[q] = a.fused ? mstep_value(a.coef, lp[i][q], s) : s;
 			}
 			if(!a.fused) {
-				if(a.sstats32) {
+				if(a.peer_ranks > 0) {
+					int64_t off;
+					void* dst = peer_column(a, w, &off);
+					if(a.peer_elem == 4) {
+						reinterpret_cast<float4*>(static_cast<float*>(dst) + off)[c] = make_float4((float) lam[0], (float) lam[1], (float) lam[2], (float) lam[3]);
+					} else {
+						double2* out = reinterpret_cast<double2*>(static_cast<double*>(dst) + off) + 2 * c;
+						out[0] = make_double2(lam[0], lam[1]);
+						out[1] = make_double2(lam[2], lam[3]);
+					}
+				} else if(a.sstats32) {
 					reinterpret_cast<float4*>(a.sstats32 + base)[c] = make_float4((float) lam[0], (float) lam[1], (float) lam[2], (float) lam[3]);
 				} else {
 					double2* out = reinterpret_cast<double2*>(a.sstats + base) + 2 * c;
@@ -842,15 +872,18 @@ __global__ void __launch_bounds__(256) k_mstep_shard(ShardMStepArgs a) {
 			for(int q = 0; q < 4; ++q)
 				ek[q] = c == (int) threadIdx.x ? ek0[q] : ((sizeof(TB) == 4 && a.write_beta && !a.psi_partials) ? (float) exp(-a.psi_rows[4 * c + q]) : 0.f);
 			// pull: all ranks' partial columns in flight at once, summed in rank order (deterministic)
+			// the G partial columns of this word, pushed here by the scatter kernels of all ranks; rank order
 			double s4[4] = {0.0, 0.0, 0.0, 0.0};
+			const int64_t slot = (int64_t) (w - a.v0) * K;
+			const int64_t stride = (int64_t) a.shard_cap * K;
 			if constexpr(sizeof(TS) == 8) {
 				double2 part[TRLDA_MAX_RANKS][2];
 				#pragma unroll
 				for(int r = 0; r < TRLDA_MAX_RANKS; ++r)
 					if(r < G) {
-						const double2* src = reinterpret_cast<const double2*>(static_cast<const double*>(a.sstats[r]) + base) + 2 * c;
-						part[r][0] = src[0];
-						part[r][1] = src[1];
+						const double2* src = reinterpret_cast<const double2*>(static_cast<const double*>(a.partials) + r * stride + slot) + 2 * c;
+						part[r][0] = __ldcs(src);
+						part[r][1] = __ldcs(src + 1);
 					}
 				#pragma unroll
 				for(int r = 0; r < TRLDA_MAX_RANKS; ++r)
@@ -862,7 +895,7 @@ __global__ void __launch_bounds__(256) k_mstep_shard(ShardMStepArgs a) {
 				#pragma unroll
 				for(int r = 0; r < TRLDA_MAX_RANKS; ++r)
 					if(r < G)
-						part[r] = reinterpret_cast<const float4*>(static_cast<const float*>(a.sstats[r]) + base)[c];
+						part[r] = __ldcs(reinterpret_cast<const float4*>(static_cast<const float*>(a.partials) + r * stride + slot) + c);
 				#pragma unroll
 				for(int r = 0; r < TRLDA_MAX_RANKS; ++r)
 					if(r < G) {

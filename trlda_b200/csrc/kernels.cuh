@@ -104,6 +104,8 @@ bool stream_estep_applicable(int K, int n_max, int elem_size, int smem_optin);
 void launch_estep_stream(const EStepArgs& args, const DeviceDocs& docs, const int32_t* order, int64_t offset,
                          int64_t count, int n_max, int elem_size, cudaStream_t s);
 
+constexpr int TRLDA_MAX_RANKS = 8;    // one NVSwitch node
+
 // segmented scatter.  If `fused`, lambda/beta are rebuilt in the same pass (single-GPU path); else the dense
 // K x V statistics are written to `sstats`.
 struct ScatterArgs {
@@ -114,7 +116,11 @@ struct ScatterArgs {
 	void* beta = nullptr;             // K x V in (old) / out (new, if write_beta)
 	int beta_elem = 8;
 	double* sstats = nullptr;         // dense output (unfused)
-	float* sstats32 = nullptr;        // dense output rounded to float32 (mixed-mode exchange between GPUs), instead of sstats
+	float* sstats32 = nullptr;        // dense output rounded to float32, instead of sstats
+	// multi-GPU push: instead of a local dense matrix, word w's partial column is stored straight into the memory of
+	// the rank that owns w (NVLink peer store), at slot [this rank][w - first word of the owner]
+	int peer_ranks = 0, peer_rank = 0, peer_shard_cap = 0, peer_elem = 8;
+	void* peer_out[TRLDA_MAX_RANKS] = {};
 	// fused part
 	bool fused = false;
 	MStepCoef coef{};
@@ -140,15 +146,16 @@ struct MStepArgs {
 };
 void launch_mstep(const MStepArgs& a, cudaStream_t s);
 
-// Multi-GPU M-step over NVLink peer memory: this rank owns the words [v0, v1).  For each of them the kernel PULLS the
-// partial sufficient statistics of every rank (peer loads), sums them in rank order, blends with lambda', and PUSHES
-// the new expElogbeta column (and, on request, the new lambda column) into every rank's replica (peer stores):
-// reduce-scatter + M-step + beta-prep + all-gather in one kernel, no intermediate K x V buffer, no NCCL on the data.
-constexpr int TRLDA_MAX_RANKS = 8;    // one NVSwitch node
+// Multi-GPU M-step over NVLink peer memory: this rank owns the words [v0, v1).  The scatter kernels of all ranks have
+// PUSHED their partial columns for these words into this rank's receive buffer (peer stores, overlapped with the
+// scatter itself); this kernel sums the partials in rank order, blends with lambda', and PUSHES the new expElogbeta
+// column (and, on request, the new lambda column) into every rank's replica: reduce-scatter + M-step + beta-prep +
+// all-gather without an intermediate K x V matrix and without NCCL on the data path.
 struct ShardMStepArgs {
 	int K = 0, V = 0, v0 = 0, v1 = 0, nranks = 1, rank = 0;
 	MStepCoef coef{};
-	const void* sstats[TRLDA_MAX_RANKS] = {};     // every rank's local dense statistics (peer-mapped), float64 or float32
+	const void* partials = nullptr;               // LOCAL receive buffer [nranks][shard_cap][K] filled by the peers' scatter kernels
+	int shard_cap = 0;
 	int sstats_elem = 8;
 	void* beta[TRLDA_MAX_RANKS] = {};             // every rank's expElogbeta replica
 	double* lambda[TRLDA_MAX_RANKS] = {};         // every rank's target lambda buffer

@@ -237,8 +237,8 @@ struct trlda_model {
 	int rank = 0, nranks = 1;
 	// peer-mapped replicas (cudaIpc) for the fused reduce-scatter + M-step + all-gather kernel: [rank] pointers to
 	// every rank's sstats, beta and the two lambda buffers; peer_ready once the handles have been exchanged
-	DevBuf sstats32;                           // float32 partial statistics for the peer exchange in mixed mode
-	int peer_sstats_elem = 8;
+	DevBuf sstats32;                           // receive buffer of the peer exchange: partial columns pushed by all ranks
+	int peer_sstats_elem = 8, peer_shard_cap = 0;
 	bool lambda_sharded = false;               // debug: the last M-step left lambda complete only on the owners' shards
 	bool peer_ready = false;
 	bool use_peer = true;                      // TRLDA_MULTI_GPU=allreduce selects the plain NCCL all-reduce path
@@ -758,8 +758,7 @@ int ensure_csc(trlda_model* m) {
 // dense sufficient statistics of the last E-step (summed over ranks) -> sstats   (lda.cpp:207-217)
 int run_scatter_dense(trlda_model* m, bool reduce_over_ranks = true, bool for_peers = false) {
 	TRY(ensure_csc(m));
-	const bool as_float = for_peers && m->peer_sstats_elem == 4;
-	if(!as_float)
+	if(!for_peers)
 		CUDA_TRY(m, m->sstats.ensure(kv_bytes(m)));
 	ScatterArgs a;
 	a.K = m->K;
@@ -770,7 +769,14 @@ int run_scatter_dense(trlda_model* m, bool reduce_over_ranks = true, bool for_pe
 	a.beta = m->beta.p;
 	a.beta_elem = m->beta_elem;
 	a.sstats = m->sstats.as<double>();
-	a.sstats32 = as_float ? m->sstats32.as<float>() : nullptr;
+	if(for_peers) {
+		a.peer_ranks = m->nranks;
+		a.peer_rank = m->rank;
+		a.peer_shard_cap = m->peer_shard_cap;
+		a.peer_elem = m->peer_sstats_elem;
+		for(int r = 0; r < m->nranks; ++r)
+			a.peer_out[r] = m->peer_sstats[r];
+	}
 	a.fused = false;
 	{
 		Launch l(m, KK_SCATTER);
@@ -830,10 +836,11 @@ int run_mstep(trlda_model* m, const MStepCoef& coef, const double* prime, double
 		sa.rank = m->rank;
 		sa.coef = coef;
 		for(int r = 0; r < m->nranks; ++r) {
-			sa.sstats[r] = m->peer_sstats[r];
 			sa.beta[r] = m->peer_beta[r];
 			sa.lambda[r] = static_cast<double*>(m->peer_lam[target_index][r]);
 		}
+		sa.partials = m->sstats32.p;
+		sa.shard_cap = m->peer_shard_cap;
 		sa.sstats_elem = m->peer_sstats_elem;
 		sa.lambda_prime = prime;
 		sa.psi_rows = m->psi_rows.as<double>();
@@ -1749,11 +1756,10 @@ int trlda_comm_init(trlda_model* m, const void* id_bytes, int rank, int nranks) 
 	CUDA_TRY(m, m->lam[1 - m->cur].ensure(kv_bytes(m)));
 	// mixed mode exchanges the per-rank partial statistics rounded to float32 (they are summed in float64)
 	m->peer_sstats_elem = (m->beta_elem == 4 && m->K % 4 == 0) ? 4 : 8;
-	if(m->peer_sstats_elem == 4)
-		CUDA_TRY(m, m->sstats32.ensure(kv_bytes(m) / 2));
-	else
-		CUDA_TRY(m, m->sstats.ensure(kv_bytes(m)));
-	void* mine[4] = {m->peer_sstats_elem == 4 ? m->sstats32.p : m->sstats.p, m->beta.p, m->lam[0].p, m->lam[1].p};
+	// receive buffer for the pushed partial columns: [nranks][shard_cap][K]
+	m->peer_shard_cap = (m->V + nranks - 1) / nranks + 1;
+	CUDA_TRY(m, m->sstats32.ensure((size_t) nranks * m->peer_shard_cap * m->K * m->peer_sstats_elem));
+	void* mine[4] = {m->sstats32.p, m->beta.p, m->lam[0].p, m->lam[1].p};
 	std::vector<cudaIpcMemHandle_t> handles((size_t) 4 * nranks);
 	cudaIpcMemHandle_t local[4];
 	for(int i = 0; i < 4; ++i)
