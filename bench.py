@@ -126,12 +126,23 @@ class ClockSampler(object):
 			'samples': len(sm), 'reasons': sorted(reasons)}
 
 
-def make_inputs(w, batch, rank, workload_name):
+def make_inputs(w, batch, rank, workload_name, num_batches=1):
+	"""`num_batches` minibatches of `batch` documents each, drawn from ONE synthetic corpus (same topics), as one CSR
+	triple; plus the initial lambda."""
 	from trlda_b200.synth import gamma_matrix, make_corpus
 	cfg = CFG_INDEX[workload_name]
-	ptr, ids, cts = make_corpus(batch, w['V'], w['K'], w['alpha'], w['eta'], seed=1000 + cfg + 7919 * rank)
+	ptr, ids, cts = make_corpus(batch * num_batches, w['V'], w['K'], w['alpha'], w['eta'], seed=1000 + cfg + 7919 * rank)
 	lam0 = gamma_matrix(w['K'], w['V'], 2000 + cfg)          # identical on every rank (replicated model)
 	return (ptr, ids, cts), lam0
+
+
+def split_batches(docs, batch, num_batches):
+	ptr, ids, cts = docs
+	out = []
+	for i in range(num_batches):
+		lo, hi = ptr[i * batch], ptr[(i + 1) * batch]
+		out.append((ptr[i * batch:(i + 1) * batch + 1] - lo, ids[lo:hi], cts[lo:hi]))
+	return out
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -266,9 +277,14 @@ def main():
 		return float(t.item())
 
 	K, V, B = w['K'], w['V'], w['B']
-	docs_np, lam0 = make_inputs(w, B, rank, args.workload)
-	docs = capi.CSR(*docs_np)
-	N = docs.num_pairs
+	# Every step (warm-up and timed) gets a minibatch the model has never seen, as in real online training: the first
+	# E-step of a step then starts from a fresh gamma against documents lambda has not been fitted to.
+	num_batches = min(args.steps + args.warmup, 32)
+	docs_all, lam0 = make_inputs(w, B, rank, args.workload, num_batches)
+	batches_np = split_batches(docs_all, B, num_batches)
+	batches = [capi.CSR(*b) for b in batches_np]
+	docs_np = batches_np[0]
+	N = int(np.mean([b.num_pairs for b in batches]))
 
 	model = capi.Model('online', V, K, w['D'], w['alpha'], w['eta'], device=local_rank, precision=args.precision)
 	model.lambdas = lam0
@@ -280,9 +296,13 @@ def main():
 	params = dict(w['params'])
 
 	# ---- device-resident leg: `value` ----------------------------------------------------------------------------------
-	model.upload_docs(docs)
+	for i, b in enumerate(batches):
+		model.upload_docs_slot(b, i)
+	step_index = 0
 	for _ in range(args.warmup):
+		model.select_docs(step_index % num_batches)
 		model.update_parameters_resident(**params)
+		step_index += 1
 	model.set_profiling(True)
 	model.reset_stats()
 	sampler = ClockSampler(local_rank)
@@ -292,7 +312,9 @@ def main():
 	e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 	e0.record(stream)
 	for _ in range(args.steps):
+		model.select_docs(step_index % num_batches)
 		model.update_parameters_resident(**params)
+		step_index += 1
 	e1.record(stream)
 	torch.cuda.synchronize()
 	barrier()
@@ -302,17 +324,23 @@ def main():
 	model.set_profiling(False)
 
 	# ---- end-to-end leg: host CSR buffers -> C ABI -> D2H of the step's result -----------------------------------------
+	# the model is reset so that the same minibatches are unseen again
+	model.lambdas = lam0
+	model.update_count = 0
 	model.reset_stats()
+	step_index = 0
 	for _ in range(min(args.warmup, 2)):
-		model.update_parameters(docs, **params)
+		model.update_parameters(batches[step_index % num_batches], **params)
 		model.row_sums()
+		step_index += 1
 	model.reset_stats()
 	barrier()
 	torch.cuda.synchronize()
 	t0 = time.perf_counter()
 	for _ in range(args.steps):
-		model.update_parameters(docs, **params)
+		model.update_parameters(batches[step_index % num_batches], **params)
 		result = model.row_sums()
+		step_index += 1
 	torch.cuda.synchronize()
 	barrier()
 	e2e_s = max_over_ranks(time.perf_counter() - t0) / args.steps
@@ -349,6 +377,7 @@ def main():
 		'data': 'synthetic',
 		'config': {
 			'workload': w['desc'], 'global_batch': global_batch, 'docs_per_gpu': B, 'pairs_per_gpu': N,
+			'minibatches': '%d distinct minibatches of one synthetic corpus, one per step: every step sees unseen documents' % num_batches,
 			'precision': args.precision, 'parallelism': ('single GPU' if world == 1 else 'docs sharded over %d GPUs; per TR iteration one fused reduce-scatter + M-step + all-gather of beta over NVLink peer memory' % world),
 			'l2': 'no flush needed: every step streams lambda/beta (%.1f GB working set >> 126 MB L2)' % (
 				K * V * (16 + s_bytes) / 1e9)},

@@ -148,6 +148,11 @@ TRLDA_API int trlda_update_parameters(trlda_model* m, const trlda_docs* docs, co
 /* Same as trlda_update_parameters but on the minibatch already resident in HBM (trlda_upload_docs): the
  * device-only leg of bench.py.  No host<->device traffic except the returned scalar. */
 TRLDA_API int trlda_upload_docs(trlda_model* m, const trlda_docs* docs);
+/* Several minibatches can be kept resident at once: upload into a numbered slot (0..63), then make one of them the
+ * current minibatch before trlda_update_parameters_resident.  Used by bench.py so that every timed step sees a
+ * minibatch the model has not been trained on, without host<->device traffic in the device-only leg. */
+TRLDA_API int trlda_upload_docs_slot(trlda_model* m, const trlda_docs* docs, int slot);
+TRLDA_API int trlda_select_docs(trlda_model* m, int slot);
 TRLDA_API int trlda_update_parameters_resident(trlda_model* m, const trlda_params* params, double* result);
 
 /* LDA::lowerBound (lda.cpp:297-360; OnlineLDA::lowerBound onlinelda.cpp:184-191).  Follows the INTENDED

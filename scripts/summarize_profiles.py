@@ -1,0 +1,64 @@
+"""Turns the ncu outputs brought back in gpurun_out/ into the tracked summaries under profiles/.
+
+    python scripts/summarize_profiles.py <launches.csv> <full.ncu-rep> <tag>
+"""
+import collections, csv, os, subprocess, sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+launches, rep, tag = sys.argv[1:4]
+
+# ---- launch list: per-kernel totals and shares -----------------------------------------------------------------------
+with open(launches) as f:
+	lines = [l for l in f if not l.startswith('==')]
+rows = list(csv.DictReader(lines))
+out_csv = os.path.join(ROOT, 'profiles', '%s_launches.csv' % tag)
+with open(out_csv, 'w') as f:
+	w = csv.writer(f)
+	w.writerow(['id', 'kernel', 'grid', 'block', 'duration_ms'])
+	for r in rows:
+		w.writerow([r['ID'], r['Kernel Name'].split('(')[0].replace('void ', '').replace('trlda::', ''), r['Grid Size'], r['Block Size'],
+			'%.4f' % (float(r['Metric Value'].replace(',', '')) / 1e6)])
+total = collections.Counter()
+count = collections.Counter()
+for r in rows:
+	name = r['Kernel Name'].split('(')[0].replace('void ', '').replace('trlda::', '')
+	total[name] += float(r['Metric Value'].replace(',', '')) / 1e6
+	count[name] += 1
+grand = sum(total.values())
+summary = ['# %s — ncu launch list of `python bench.py --steps 2 --warmup 1 --no-cpu-baseline`' % tag,
+	'(`ncu --metrics gpu__time_duration.sum --clock-control none`; cold-cache, serialised: compare shares)', '',
+	'| kernel | launches | total ms | share | mean ms |', '|---|---:|---:|---:|---:|']
+for name, ms in total.most_common():
+	summary.append('| `%s` | %d | %.2f | %.1f %% | %.3f |' % (name, count[name], ms, 100 * ms / grand, ms / count[name]))
+summary.append('| all | %d | %.2f | 100 %% | |' % (len(rows), grand))
+
+# ---- full capture: key metrics per captured launch --------------------------------------------------------------------
+raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+data = list(csv.reader(raw.splitlines()))
+hdr, units, body = data[0], data[1], data[2:]
+idx = {h: i for i, h in enumerate(hdr)}
+keys = ['Kernel Name', 'Grid Size', 'Block Size', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
+	'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'lts__throughput.avg.pct_of_peak_sustained_elapsed',
+	'lts__t_sector_hit_rate.pct', 'l1tex__m_xbar2l1tex_read_bytes.sum', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
+	'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__warps_active.avg.pct_of_peak_sustained_active',
+	'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active', 'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active',
+	'smsp__inst_executed.sum', 'launch__registers_per_thread', 'launch__occupancy_limit_registers',
+	'launch__occupancy_limit_shared_mem', 'launch__shared_mem_per_block_dynamic']
+with open(os.path.join(ROOT, 'profiles', '%s_ncu_full.csv' % tag), 'w') as f:
+	w = csv.writer(f)
+	w.writerow(['metric', 'unit'] + ['launch%d' % i for i in range(len(body))])
+	for k in keys:
+		if k in idx:
+			w.writerow([k, units[idx[k]]] + [r[idx[k]] for r in body])
+summary += ['', '## `ncu --set full` capture (%s_ncu_full.csv)' % tag, '',
+	'| launch | kernel | ms | DRAM read GB | DRAM write GB | DRAM %% of peak | L2 hit %% | issue active %% | regs |', '|---|---|---:|---:|---:|---:|---:|---:|---:|']
+for i, r in enumerate(body):
+	g = lambda k: r[idx[k]] if k in idx else ''
+	summary.append('| %d | `%s` | %.3f | %.3f | %.3f | %.1f | %.1f | %.1f | %s |' % (
+		i, g('Kernel Name').split('(')[0].replace('void ', '').replace('trlda::', ''), float(g('gpu__time_duration.sum')),
+		float(g('dram__bytes_read.sum')), float(g('dram__bytes_write.sum')),
+		float(g('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed')), float(g('lts__t_sector_hit_rate.pct')),
+		float(g('smsp__issue_active.avg.pct_of_peak_sustained_active')), g('launch__registers_per_thread')))
+with open(os.path.join(ROOT, 'profiles', '%s_summary.md' % tag), 'w') as f:
+	f.write('\n'.join(summary) + '\n')
+print('\n'.join(summary))

@@ -96,6 +96,8 @@ PROTOTYPES = {
 	'trlda_update_variables': (C.c_int, [C.c_void_p, _P(Docs), _dbl, C.c_int, C.c_int64, _P(Params), _dbl, _dbl]),
 	'trlda_update_parameters': (C.c_int, [C.c_void_p, _P(Docs), _P(Params), _dbl]),
 	'trlda_upload_docs': (C.c_int, [C.c_void_p, _P(Docs)]),
+	'trlda_upload_docs_slot': (C.c_int, [C.c_void_p, _P(Docs), C.c_int]),
+	'trlda_select_docs': (C.c_int, [C.c_void_p, C.c_int]),
 	'trlda_update_parameters_resident': (C.c_int, [C.c_void_p, _P(Params), _dbl]),
 	'trlda_lower_bound': (C.c_int, [C.c_void_p, _P(Docs), _dbl, C.c_int, C.c_int64, _P(Params), C.c_int64, _dbl, _dbl]),
 	'trlda_inject_initial_gamma': (C.c_int, [C.c_void_p, _dbl, C.c_int, C.c_int64]),
@@ -319,6 +321,12 @@ class Model(object):
 
 	def upload_docs(self, docs):
 		self._check(self._lib.trlda_upload_docs(self.h, C.byref(docs.c)))
+
+	def upload_docs_slot(self, docs, slot):
+		self._check(self._lib.trlda_upload_docs_slot(self.h, C.byref(docs.c), int(slot)))
+
+	def select_docs(self, slot):
+		self._check(self._lib.trlda_select_docs(self.h, int(slot)))
 
 	def update_parameters_resident(self, gamma0=None, lambda0=None, **kwargs):
 		self.inject(gamma0, lambda0)

@@ -1,22 +1,27 @@
-// estep_stream.cu — the per-document E-step (lda.cpp:174-204 of the reference) for WARM-STARTED documents.
+// estep_stream.cu — the per-document E-step (lda.cpp:174-204 of the reference), streaming design (the default path).
 //
-// In trust-region iterations >= 1 the fixed point restarts from the previous iteration's gamma
-// (onlinelda.cpp:91-93) and almost every document converges after one or two inner iterations.  For such
-// documents keeping the K x n_d tile resident (estep_fast.cu) buys nothing: the cost is the gather plus a few
-// latency-bound phases.  This kernel instead STREAMS the tile: one CTA owns a whole document (all K rows), every
-// warp pulls its own columns of expElogbeta through a private shared-memory ring with `cp.async` (no block-wide
-// barrier on the data path), and — because a warp sees a complete column — the two passes of the reference's
-// inner iteration fuse into ONE sweep:
+// The K x n_d tile of expElogbeta columns of a document is NOT kept on chip; it is streamed once per inner iteration:
+// every warp pulls its own columns (K contiguous values each) through a private shared-memory ring with 16-byte
+// `cp.async` (no block-wide barrier on the data path), and — because a warp sees a complete column — the two passes
+// of the reference's inner iteration fuse into ONE sweep:
 //
 //     phi_j = etheta . col_j  (+1e-100)      lda.cpp:183,199      warp-shuffle reduction over the K rows
 //     W_j   = c_j / phi_j                    lda.cpp:192
 //     acc  += W_j col_j                      lda.cpp:189-193      lane-local: every lane keeps its rows in registers
 //
 // After a sweep the per-warp partial sums meet in shared memory (fixed order: deterministic), gamma and
-// exp(psi(gamma)) are updated (lda.cpp:194-197) and the convergence test of lda.cpp:202 is CTA-local: no
-// cluster, no DSMEM.  An inner iteration costs one sweep over the document's columns, which the 126 MB L2
-// serves from the second sweep on; I inner iterations cost I+1 sweeps (the last one produces the token weights
-// and the document's share of the row sums of the sufficient statistics).
+// exp(psi(gamma)) are updated (lda.cpp:194-197) and the convergence test of lda.cpp:202 is evaluated.  I inner
+// iterations cost I+1 sweeps (the last one produces the token weights and the document's share of the row sums of
+// the sufficient statistics); the first sweep comes from HBM, the re-sweeps should come from L2.
+//
+// That last point decides the shape.  With one document per SM the tiles in flight are 148 x ~600 KB at cfg-3 —
+// more than the L2 keeps (ncu: 77 % of the re-sweep bytes came from DRAM).  So a document is given to a CLUSTER of
+// C CTAs (C = 2 by default) that split its COLUMNS: each SM streams 1/C of the tile, the tiles in flight shrink to
+// 148 x 600/C KB and stay L2-resident, and the only cross-CTA traffic per sweep is one K-vector of partial sums,
+// sent to every peer with one DSMEM bulk copy (`cp.async.bulk.shared::cluster.shared::cta`) that completes on the
+// receiver's mbarrier.  Every CTA adds the C partial vectors in rank order — identical bits everywhere — and
+// updates gamma / exp(psi(gamma)) redundantly, so the convergence decision is cluster-uniform without further
+// exchange and the result does not depend on timing.
 #include "kernels.cuh"
 #include "special.cuh"
 
@@ -35,10 +40,10 @@ __device__ __forceinline__ void svec_get(const double2& v, double (&o)[2]) { o[0
 constexpr int STREAM_DEPTH = 2;   // columns in flight per warp
 
 struct StreamSmem {
-	size_t ring, red, eth, gam, wsum, wid, cnt, total;
+	size_t ring, red, eth, gam, wsum, xstage, xall, wid, cnt, bar, total;
 };
 
-__host__ __device__ inline StreamSmem stream_smem_layout(int NW, int kp, int n_cap, int elem) {
+__host__ __device__ inline StreamSmem stream_smem_layout(int NW, int C, int kp, int n_cap, int elem) {
 	StreamSmem L;
 	size_t o = 0;
 	auto take = [&o](size_t bytes) { size_t at = o; o += (bytes + 15) & ~size_t(15); return at; };
@@ -47,15 +52,15 @@ __host__ __device__ inline StreamSmem stream_smem_layout(int NW, int kp, int n_c
 	L.eth = take((size_t) kp * elem);
 	L.gam = take((size_t) kp * 8);
 	L.wsum = take((size_t) NW * 8);
+	L.xstage = take(C > 1 ? (size_t) 2 * kp * 8 : 0);             // [2] outgoing partial vector
+	L.xall = take(C > 1 ? (size_t) 2 * C * kp * 8 : 0);           // [2][C] incoming partial vectors
 	L.wid = take((size_t) n_cap * 4);
 	L.cnt = take((size_t) n_cap * 4);
+	L.bar = take(32);
 	L.total = o;
 	return L;
 }
 
-static bool g_stream_shuffle = false; // TRLDA_STREAM_SHUFFLE=1: strided document order (measured: no gain over longest-first)
-static int g_stream_warps_f32 = 8;    // TRLDA_STREAM_WARPS: 8 (two CTAs per SM, default) or 16 (one)
-static inline int stream_warps(int elem) { return elem == 4 ? g_stream_warps_f32 : 8; }
 static inline int stream_nvec(int K, int elem) {
 	const int per_sweep = 32 * (16 / elem);
 	int nvec = 1;
@@ -64,7 +69,25 @@ static inline int stream_nvec(int K, int elem) {
 	return nvec;
 }
 
-// applicable?  (aligned columns, K small enough for the per-lane register tile, word ids fit in shared memory)
+// launch shape: (cluster size, warps per CTA).  TRLDA_STREAM_CLUSTER / TRLDA_STREAM_WARPS override.
+static void stream_shape(int elem, int* cluster, int* warps) {
+	int C = 2, NW = elem == 4 ? 8 : 4;
+	if(const char* e = getenv("TRLDA_STREAM_CLUSTER"))
+		C = atoi(e) == 1 ? 1 : (atoi(e) == 4 ? 4 : 2);
+	if(C == 1)
+		NW = 8;
+	if(const char* e = getenv("TRLDA_STREAM_WARPS")) {
+		const int w = atoi(e);
+		if(w == 4 || w == 8 || (w == 16 && elem == 4 && C == 1))
+			NW = w;
+	}
+	if(elem == 8 && C > 1 && NW > 4)
+		NW = 4;
+	*cluster = C;
+	*warps = NW;
+}
+
+// applicable?  (aligned columns, K small enough for the per-lane register tile, everything fits in shared memory)
 bool stream_estep_applicable(int K, int n_max, int elem, int smem_optin) {
 	if((K * elem) % 16 != 0)
 		return false;
@@ -73,37 +96,70 @@ bool stream_estep_applicable(int K, int n_max, int elem, int smem_optin) {
 		return false;
 	const int kp = nvec * 32 * (16 / elem);
 	const int n_cap = std::max(32, (n_max + 31) / 32 * 32);
-	return stream_smem_layout(stream_warps(elem), kp, n_cap, elem).total <= (size_t) smem_optin - 1024;
+	int C, NW;
+	stream_shape(elem, &C, &NW);
+	return stream_smem_layout(NW, C, kp, n_cap, elem).total <= (size_t) smem_optin - 1024;
 }
 
-template <typename T, int NW, int NVEC>
-__global__ void __launch_bounds__(NW * 32, (NW == 4 ? 3 : (NW == 8 && sizeof(T) == 4 ? 2 : 1)))
-k_estep_stream(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, int64_t doc_offset, int n_cap,
-               unsigned stride, unsigned count) {
+__device__ __forceinline__ uint32_t s_smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint32_t s_map_to_rank(uint32_t smem_addr, int rank) {
+	uint32_t remote;
+	asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_addr), "r"(rank));
+	return remote;
+}
+
+__device__ __forceinline__ void s_mbar_wait(uint32_t bar, uint32_t parity) {
+	uint32_t done = 0;
+	while(!done)
+		asm volatile(
+			"{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+			: "=r"(done) : "r"(bar), "r"(parity) : "memory");
+}
+
+template <typename T, int NW, int NVEC, int C>
+__global__ void __launch_bounds__(NW * 32, (C == 1 && NW == 4 ? 3 : (C == 1 && NW == 8 && sizeof(T) == 4 ? 2 : 1)))
+k_estep_stream(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, int64_t doc_offset, int n_cap) {
 	extern __shared__ __align__(128) unsigned char smem[];
 	using V = typename SVec<T>::type;
 	constexpr int VN = SVec<T>::N;
 	constexpr int KP = NVEC * 32 * VN;                       // padded number of topic rows
 	constexpr int NT = NW * 32;
-	const StreamSmem L = stream_smem_layout(NW, KP, n_cap, (int) sizeof(T));
+	constexpr int TW = NW * C;                               // warps working on one document
+	const StreamSmem L = stream_smem_layout(NW, C, KP, n_cap, (int) sizeof(T));
 	T* ring = reinterpret_cast<T*>(smem + L.ring);
 	T* red = reinterpret_cast<T*>(smem + L.red);
 	T* eth = reinterpret_cast<T*>(smem + L.eth);
 	double* gam = reinterpret_cast<double*>(smem + L.gam);
 	double* wsum = reinterpret_cast<double*>(smem + L.wsum);
+	double* xstage = reinterpret_cast<double*>(smem + L.xstage);
+	double* xall = reinterpret_cast<double*>(smem + L.xall);
 	int* wid = reinterpret_cast<int*>(smem + L.wid);
 	int* cnt = reinterpret_cast<int*>(smem + L.cnt);
+	uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.bar);
 
-	// CTA i takes the (i * stride mod count)-th longest document: every wave of CTAs then holds a mix of lengths, the
-	// CTAs drift out of phase, and the HBM-bound first sweep of one document overlaps the L2-bound re-sweeps and
-	// psi phases of its neighbours instead of all CTAs hitting HBM (then L2) in lockstep
-	const int64_t slot = doc_offset + (int64_t) (((uint64_t) blockIdx.x * stride) % count);
+	int rank = 0;
+	if(C > 1)
+		asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+	const int64_t slot = doc_offset + blockIdx.x / C;
 	const int64_t d = order ? order[slot] : slot;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int gw = rank * NW + warp;                          // this warp's index among the document's warps
 	const int K = a.K;
 	const int64_t begin = docs.doc_ptr[d];
 	const int n = (int) (docs.doc_ptr[d + 1] - begin);
 	const T* __restrict__ beta = static_cast<const T*>(a.beta);
+
+	if(C > 1) {
+		if(tid == 0) {
+			asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s_smem_u32(bar)));
+			asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s_smem_u32(bar + 1)));
+			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		}
+		__syncthreads();
+		// start-up cluster barrier (exchange barriers initialised everywhere): arrive now, wait before the first push
+		asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+	}
 
 	for(int j = tid; j < n; j += NT) {
 		wid[j] = docs.word_ids[begin + j];
@@ -113,7 +169,7 @@ k_estep_stream(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, 
 		double g = 0.0, e = 0.0;
 		if(r < K) {
 			g = a.gamma[d * K + r];
-			e = exp_digamma_for<T>(g, 0.0);                                   // lda.cpp:174
+			e = exp_digamma_for<T>(g, 0.0);                       // lda.cpp:174
 		}
 		gam[r] = g;
 		eth[r] = (T) e;
@@ -122,7 +178,7 @@ k_estep_stream(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, 
 
 	// this lane's rows: vectors v = 0..NVEC-1 cover rows (v * 32 + lane) * VN .. + VN
 	T* my_ring = ring + (size_t) warp * STREAM_DEPTH * KP;
-	const uint32_t ring_addr = (uint32_t) __cvta_generic_to_shared(my_ring);
+	const uint32_t ring_addr = s_smem_u32(my_ring);
 	auto issue = [&](int j, int stage) {                           // gather column j into ring slot `stage`
 		const T* src = beta + (int64_t) wid[j] * K;
 		#pragma unroll
@@ -134,13 +190,17 @@ k_estep_stream(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, 
 		}
 	};
 
+	const uint32_t xstage_addr = s_smem_u32(xstage), xall_addr = s_smem_u32(xall), bar_addr = s_smem_u32(bar);
+	constexpr uint32_t XBYTES = KP * 8;
+
 	int it = 0;
+	int sweep = 0;
 	bool converged = false;
 	bool primed = false;   // the ring already holds the first columns of the coming sweep
 	int stage = 0;
 	while(true) {
 		const bool final_sweep = converged || it >= a.max_iter;
-		// ---- one sweep over the document's columns: this warp takes columns warp, warp + NW, ... -----------------------
+		// ---- one sweep over the document's columns: this warp takes columns gw, gw + TW, ... ---------------------------
 		T e[NVEC][VN], acc[NVEC][VN];
 		#pragma unroll
 		for(int v = 0; v < NVEC; ++v) {
@@ -150,12 +210,12 @@ k_estep_stream(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, 
 				acc[v][q] = T(0);
 		}
 		// M = number of columns of this warp.  If the ring was not primed by the previous sweep, fill it now.
-		const int M = warp < n ? (n - warp + NW - 1) / NW : 0;
+		const int M = gw < n ? (n - gw + TW - 1) / TW : 0;
 		if(!primed) {
 			#pragma unroll
 			for(int s = 0; s < STREAM_DEPTH; ++s) {
 				if(s < M)
-					issue(warp + s * NW, s);
+					issue(gw + s * TW, s);
 				asm volatile("cp.async.commit_group;" ::: "memory");
 			}
 			stage = 0;
@@ -165,7 +225,7 @@ k_estep_stream(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, 
 		// the (L2) latency of the next sweep hides behind the reduction and the psi evaluations
 		const bool prime_next = !final_sweep && M >= STREAM_DEPTH;
 		for(int mcol = 0; mcol < M; ++mcol) {
-			const int j = warp + mcol * NW;
+			const int j = gw + mcol * TW;
 			asm volatile("cp.async.wait_group %0;" ::"n"(STREAM_DEPTH - 1) : "memory");
 			__syncwarp();
 			const T* col = my_ring + (size_t) stage * KP;
@@ -201,9 +261,9 @@ k_estep_stream(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, 
 			__syncwarp();
 			const int mn = mcol + STREAM_DEPTH;
 			if(mn < M)
-				issue(warp + mn * NW, stage);
+				issue(gw + mn * TW, stage);
 			else if(prime_next)
-				issue(warp + (mn - M) * NW, stage);
+				issue(gw + (mn - M) * TW, stage);
 			asm volatile("cp.async.commit_group;" ::: "memory");
 			stage = stage + 1 == STREAM_DEPTH ? 0 : stage + 1;
 		}
@@ -221,19 +281,56 @@ k_estep_stream(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, 
 			*reinterpret_cast<V*>(red + (size_t) warp * KP + (v * 32 + lane) * VN) = out;
 		}
 		__syncthreads();
+
+		const int buf = sweep & 1;
+		if(C > 1) {
+			// ---- cluster exchange: this CTA's partial K-vector goes to every CTA of the cluster (itself included) -------
+			if(tid == 0)
+				asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+					::"r"(bar_addr + 8 * buf), "r"((uint32_t) C * XBYTES) : "memory");
+			double* out = xstage + (size_t) buf * KP;
+			for(int r = tid; r < KP; r += NT) {
+				double partial = 0.0;
+				#pragma unroll 4
+				for(int q = 0; q < NW; ++q)
+					partial += (double) red[(size_t) q * KP + r];
+				out[r] = partial;
+			}
+			__syncthreads();
+			if(sweep == 0)
+				asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+			if(tid < C) {
+				asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+				const uint32_t dst = s_map_to_rank(xall_addr + (uint32_t) ((buf * C + rank) * XBYTES), tid);
+				const uint32_t dst_bar = s_map_to_rank(bar_addr + 8 * buf, tid);
+				asm volatile(
+					"cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+					::"r"(dst), "r"(xstage_addr + (uint32_t) buf * XBYTES), "r"(XBYTES), "r"(dst_bar) : "memory");
+			}
+			s_mbar_wait(bar_addr + 8 * buf, (uint32_t) ((sweep >> 1) & 1));
+		}
+
 		double delta_local = 0.0;
 		for(int r = tid; r < K; r += NT) {
 			double total = 0.0;
-			#pragma unroll 4
-			for(int q = 0; q < NW; ++q)
-				total += (double) red[(size_t) q * KP + r];
+			if(C > 1) {
+				#pragma unroll
+				for(int src = 0; src < C; ++src)
+					total += xall[(size_t) (buf * C + src) * KP + r];      // rank order: identical bits in every CTA
+			} else {
+				#pragma unroll 4
+				for(int q = 0; q < NW; ++q)
+					total += (double) red[(size_t) q * KP + r];
+			}
 			const double eo = (double) eth[r];
 			if(final_sweep) {
-				a.doc_stat[d * K + r] = total * eo;
-				a.gamma[d * K + r] = gam[r];
-				a.etheta[d * K + r] = eo;
-				if(a.etheta32)
-					a.etheta32[d * K + r] = (float) eo;
+				if(C == 1 || r % C == rank) {                          // the CTAs share the output rows
+					a.doc_stat[d * K + r] = total * eo;
+					a.gamma[d * K + r] = gam[r];
+					a.etheta[d * K + r] = eo;
+					if(a.etheta32)
+						a.etheta32[d * K + r] = (float) eo;
+				}
 			} else {                                                   // lda.cpp:186-197
 				const double g_old = gam[r];
 				double g_new = total * eo;
@@ -243,6 +340,7 @@ k_estep_stream(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, 
 				eth[r] = (T) exp_digamma_for<T>(g_new, 0.0);
 			}
 		}
+		++sweep;
 		if(final_sweep)
 			break;
 		delta_local = warp_sum(delta_local);
@@ -256,68 +354,75 @@ k_estep_stream(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, 
 		converged = delta / K < a.threshold;                           // lda.cpp:202
 		__syncthreads();
 	}
-	if(tid == 0 && a.iterations)
+	if(rank == 0 && tid == 0 && a.iterations)
 		a.iterations[d] = it;
+	if(C > 1) {
+		// nobody reads this CTA's staging buffers any more once every CTA has passed its last exchange
+		asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+		asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+	}
 }
 
-template <typename T, int NW, int NVEC>
+template <typename T, int NW, int NVEC, int C>
 static void launch_stream_t(const EStepArgs& args, const DeviceDocs& docs, const int32_t* order, int64_t offset,
                             int64_t count, int n_cap, size_t smem, cudaStream_t s) {
-	cudaFuncSetAttribute(k_estep_stream<T, NW, NVEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-	// a stride coprime to the document count visits every document exactly once
-	static const unsigned primes[4] = {7919u, 7907u, 7901u, 7883u};
-	unsigned stride = 1;
-	if(g_stream_shuffle && count > 1)
-		for(unsigned p : primes)
-			if(count % p != 0) {
-				stride = p;
-				break;
-			}
-	k_estep_stream<T, NW, NVEC><<<(unsigned) count, NW * 32, smem, s>>>(args, docs, order, offset, n_cap, stride, (unsigned) count);
+	cudaFuncSetAttribute(k_estep_stream<T, NW, NVEC, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3((unsigned) (count * C));
+	cfg.blockDim = dim3(NW * 32);
+	cfg.dynamicSmemBytes = smem;
+	cfg.stream = s;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeClusterDimension;
+	attr[0].val.clusterDim.x = C;
+	attr[0].val.clusterDim.y = 1;
+	attr[0].val.clusterDim.z = 1;
+	cfg.attrs = attr;
+	cfg.numAttrs = C > 1 ? 1 : 0;
+	cudaLaunchKernelEx(&cfg, k_estep_stream<T, NW, NVEC, C>, args, docs, order, offset, n_cap);
+}
+
+template <typename T, int NW, int C>
+static void launch_stream_v(int nvec, const EStepArgs& args, const DeviceDocs& docs, const int32_t* order, int64_t offset,
+                            int64_t count, int n_cap, size_t smem, cudaStream_t s) {
+	constexpr int MAXV = sizeof(T) == 4 ? 8 : 16;
+	switch(nvec) {
+		case 1: launch_stream_t<T, NW, 1, C>(args, docs, order, offset, count, n_cap, smem, s); break;
+		case 2: launch_stream_t<T, NW, 2, C>(args, docs, order, offset, count, n_cap, smem, s); break;
+		case 4: launch_stream_t<T, NW, 4, C>(args, docs, order, offset, count, n_cap, smem, s); break;
+		case 8: launch_stream_t<T, NW, 8, C>(args, docs, order, offset, count, n_cap, smem, s); break;
+		default: launch_stream_t<T, NW, MAXV, C>(args, docs, order, offset, count, n_cap, smem, s); break;
+	}
 }
 
 void launch_estep_stream(const EStepArgs& args, const DeviceDocs& docs, const int32_t* order, int64_t offset,
-                         int64_t count, int n_max, int elem_size, cudaStream_t s) {
+                         int64_t count, int n_max, int elem_size, bool cold, cudaStream_t s) {
+	(void) cold;
 	if(count == 0)
 		return;
-	if(const char* e = getenv("TRLDA_STREAM_SHUFFLE"))
-		g_stream_shuffle = atoi(e) != 0;
-	if(const char* e = getenv("TRLDA_STREAM_WARPS"))
-		g_stream_warps_f32 = atoi(e) == 16 ? 16 : (atoi(e) == 4 ? 4 : 8);
+	int C, NW;
+	stream_shape(elem_size, &C, &NW);
 	const int nvec = stream_nvec(args.K, elem_size);
 	const int n_cap = std::max(32, (n_max + 31) / 32 * 32);
 	const int kp = nvec * 32 * (16 / elem_size);
-	const size_t smem = stream_smem_layout(stream_warps(elem_size), kp, n_cap, elem_size).total;
-	if(elem_size == 4 && stream_warps(4) == 16) {
-		switch(nvec) {
-			case 1: launch_stream_t<float, 16, 1>(args, docs, order, offset, count, n_cap, smem, s); break;
-			case 2: launch_stream_t<float, 16, 2>(args, docs, order, offset, count, n_cap, smem, s); break;
-			case 4: launch_stream_t<float, 16, 4>(args, docs, order, offset, count, n_cap, smem, s); break;
-			default: launch_stream_t<float, 16, 8>(args, docs, order, offset, count, n_cap, smem, s); break;
-		}
-	} else if(elem_size == 4 && stream_warps(4) == 4) {
-		switch(nvec) {
-			case 1: launch_stream_t<float, 4, 1>(args, docs, order, offset, count, n_cap, smem, s); break;
-			case 2: launch_stream_t<float, 4, 2>(args, docs, order, offset, count, n_cap, smem, s); break;
-			case 4: launch_stream_t<float, 4, 4>(args, docs, order, offset, count, n_cap, smem, s); break;
-			default: launch_stream_t<float, 4, 8>(args, docs, order, offset, count, n_cap, smem, s); break;
-		}
-	} else if(elem_size == 4) {
-		switch(nvec) {
-			case 1: launch_stream_t<float, 8, 1>(args, docs, order, offset, count, n_cap, smem, s); break;
-			case 2: launch_stream_t<float, 8, 2>(args, docs, order, offset, count, n_cap, smem, s); break;
-			case 4: launch_stream_t<float, 8, 4>(args, docs, order, offset, count, n_cap, smem, s); break;
-			default: launch_stream_t<float, 8, 8>(args, docs, order, offset, count, n_cap, smem, s); break;
-		}
+	const size_t smem = stream_smem_layout(NW, C, kp, n_cap, elem_size).total;
+#define TRLDA_STREAM_CASE(TYPE, WARPS, CLUSTER) \
+	if(NW == WARPS && C == CLUSTER) { launch_stream_v<TYPE, WARPS, CLUSTER>(nvec, args, docs, order, offset, count, n_cap, smem, s); return; }
+	if(elem_size == 4) {
+		TRLDA_STREAM_CASE(float, 8, 2)
+		TRLDA_STREAM_CASE(float, 4, 2)
+		TRLDA_STREAM_CASE(float, 8, 4)
+		TRLDA_STREAM_CASE(float, 4, 4)
+		TRLDA_STREAM_CASE(float, 8, 1)
+		TRLDA_STREAM_CASE(float, 4, 1)
+		TRLDA_STREAM_CASE(float, 16, 1)
 	} else {
-		switch(nvec) {
-			case 1: launch_stream_t<double, 8, 1>(args, docs, order, offset, count, n_cap, smem, s); break;
-			case 2: launch_stream_t<double, 8, 2>(args, docs, order, offset, count, n_cap, smem, s); break;
-			case 4: launch_stream_t<double, 8, 4>(args, docs, order, offset, count, n_cap, smem, s); break;
-			case 8: launch_stream_t<double, 8, 8>(args, docs, order, offset, count, n_cap, smem, s); break;
-			default: launch_stream_t<double, 8, 16>(args, docs, order, offset, count, n_cap, smem, s); break;
-		}
+		TRLDA_STREAM_CASE(double, 4, 2)
+		TRLDA_STREAM_CASE(double, 4, 4)
+		TRLDA_STREAM_CASE(double, 8, 1)
+		TRLDA_STREAM_CASE(double, 4, 1)
 	}
+#undef TRLDA_STREAM_CASE
 }
 
 }  // namespace trlda

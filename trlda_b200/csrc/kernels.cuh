@@ -102,7 +102,7 @@ void configure_estep_fast(int smem_optin);
 // per-warp cp.async rings, one sweep per inner iteration
 bool stream_estep_applicable(int K, int n_max, int elem_size, int smem_optin);
 void launch_estep_stream(const EStepArgs& args, const DeviceDocs& docs, const int32_t* order, int64_t offset,
-                         int64_t count, int n_max, int elem_size, cudaStream_t s);
+                         int64_t count, int n_max, int elem_size, bool cold, cudaStream_t s);
 
 constexpr int TRLDA_MAX_RANKS = 8;    // one NVSwitch node
 

@@ -206,6 +206,16 @@ struct trlda_model {
 	struct Bucket { int64_t offset, count; int n_max; };
 	std::vector<Bucket> buckets;
 	bool force_generic = false;
+	// parked resident minibatches (trlda_upload_docs_slot / trlda_select_docs): the live buffers are swapped with a slot
+	struct DocSlot {
+		bool used = false;
+		DeviceDocs docs;
+		DevBuf b_doc_ptr, b_word_ids, b_counts, b_word_ptr, b_tok_doc, b_tok_src, b_order;
+		std::vector<Bucket> buckets;
+		int64_t docs_total_count = 0, global_B = 0;
+	};
+	std::vector<DocSlot> slots;
+	int live_slot = -1;
 	// the word-sorted token list of the resident minibatch is built lazily (ensure_csc)
 	bool csc_pending = false;
 	int csc_threads = 1;
@@ -642,7 +652,7 @@ int run_estep(trlda_model* m, GammaSource src, const double* host_gamma, int max
 	   stream_estep_applicable(m->K, m->docs.n_max, m->beta_elem, m->smem_optin)) {
 		{
 			Launch l(m, KK_ESTEP);
-			launch_estep_stream(a, m->docs, m->b_order.as<int32_t>(), 0, m->docs.B, m->docs.n_max, m->beta_elem, m->stream);
+			launch_estep_stream(a, m->docs, m->b_order.as<int32_t>(), 0, m->docs.B, m->docs.n_max, m->beta_elem, !warm, m->stream);
 		}
 		m->gamma_valid = true;
 		m->stats.estep_docs = m->docs.B;
@@ -1490,6 +1500,11 @@ void trlda_destroy(trlda_model* m) {
 	                  &m->etheta32, &m->weight, &m->doc_stat, &m->iterations};
 	for(DevBuf* b : bufs)
 		b->release();
+	for(auto& slot : m->slots) {
+		DevBuf* sb[] = {&slot.b_doc_ptr, &slot.b_word_ids, &slot.b_counts, &slot.b_word_ptr, &slot.b_tok_doc, &slot.b_tok_src, &slot.b_order};
+		for(DevBuf* b : sb)
+			b->release();
+	}
 	m->staging.release();
 	m->readback.release();
 	for(int i = 0; i < trlda_model::kAuxStreams; ++i) {
@@ -1600,7 +1615,62 @@ int trlda_set_update_count(trlda_model* m, int64_t n) {
 	return TRLDA_OK;
 }
 
-int trlda_upload_docs(trlda_model* m, const trlda_docs* docs) { return upload_docs(m, docs); }
+int trlda_upload_docs(trlda_model* m, const trlda_docs* docs) {
+	m->live_slot = -1;
+	return upload_docs(m, docs);
+}
+
+namespace {
+// exchanges the live minibatch state with a parking slot (pointer swaps only)
+void swap_with_slot(trlda_model* m, trlda_model::DocSlot& slot) {
+	std::swap(m->docs, slot.docs);
+	std::swap(m->b_doc_ptr, slot.b_doc_ptr);
+	std::swap(m->b_word_ids, slot.b_word_ids);
+	std::swap(m->b_counts, slot.b_counts);
+	std::swap(m->b_word_ptr, slot.b_word_ptr);
+	std::swap(m->b_tok_doc, slot.b_tok_doc);
+	std::swap(m->b_tok_src, slot.b_tok_src);
+	std::swap(m->b_order, slot.b_order);
+	std::swap(m->buckets, slot.buckets);
+	std::swap(m->docs_total_count, slot.docs_total_count);
+	std::swap(m->global_B, slot.global_B);
+}
+}  // namespace
+
+int trlda_upload_docs_slot(trlda_model* m, const trlda_docs* docs, int slot) {
+	if(slot < 0 || slot >= 64)
+		return fail(m, TRLDA_ERR_ARG, "Minibatch slot out of range.");
+	if((int) m->slots.size() <= slot)
+		m->slots.resize(slot + 1);
+	// park the live minibatch (if it belongs to a slot), upload into fresh live buffers, finish the token list, park
+	if(m->live_slot >= 0)
+		swap_with_slot(m, m->slots[m->live_slot]);
+	m->live_slot = -1;
+	if(m->slots[slot].used)
+		swap_with_slot(m, m->slots[slot]);                     // reuse the slot's buffers
+	TRY(upload_docs(m, docs));
+	TRY(ensure_csc(m));
+	CUDA_TRY(m, cudaStreamSynchronize(m->stream));            // the pinned staging buffer is reused by the next upload
+	swap_with_slot(m, m->slots[slot]);
+	m->slots[slot].used = true;
+	m->docs_resident = false;
+	return TRLDA_OK;
+}
+
+int trlda_select_docs(trlda_model* m, int slot) {
+	if(slot < 0 || slot >= (int) m->slots.size() || !m->slots[slot].used)
+		return fail(m, TRLDA_ERR_ARG, "No minibatch has been uploaded into this slot.");
+	if(m->live_slot == slot)
+		return TRLDA_OK;
+	if(m->live_slot >= 0)
+		swap_with_slot(m, m->slots[m->live_slot]);
+	swap_with_slot(m, m->slots[slot]);
+	m->live_slot = slot;
+	m->docs_resident = true;
+	m->csc_pending = false;
+	m->gamma_valid = false;
+	return TRLDA_OK;
+}
 
 int trlda_update_variables(trlda_model* m, const trlda_docs* docs, const double* latents, int latents_rows,
                            int64_t latents_cols, const trlda_params* params, double* gamma_out, double* sstats_out) {
