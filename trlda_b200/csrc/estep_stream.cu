@@ -37,7 +37,13 @@ template <> struct SVec<double> { using type = double2; static constexpr int N =
 __device__ __forceinline__ void svec_get(const float4& v, float (&o)[4]) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
 __device__ __forceinline__ void svec_get(const double2& v, double (&o)[2]) { o[0] = v.x; o[1] = v.y; }
 
-constexpr int STREAM_DEPTH = 2;   // columns in flight per warp
+// columns in flight per warp: a cluster CTA has fewer columns per warp and reads them from L2, it needs a deeper ring
+__host__ __device__ constexpr int stream_depth(int C) { return 2; }
+
+// how many per-warp partial vectors meet in shared memory at once: above 32 KB the warps fold pairwise first
+__host__ __device__ constexpr int stream_reduce_width(int NW, int kp, int elem) {
+	return (NW * kp * elem > 32768 && NW % 2 == 0) ? NW / 2 : NW;
+}
 
 struct StreamSmem {
 	size_t ring, red, eth, gam, wsum, xstage, xall, wid, cnt, bar, total;
@@ -47,13 +53,13 @@ __host__ __device__ inline StreamSmem stream_smem_layout(int NW, int C, int kp, 
 	StreamSmem L;
 	size_t o = 0;
 	auto take = [&o](size_t bytes) { size_t at = o; o += (bytes + 15) & ~size_t(15); return at; };
-	L.ring = take((size_t) NW * STREAM_DEPTH * kp * elem);
-	L.red = take((size_t) NW * kp * elem);
+	L.ring = take((size_t) NW * stream_depth(C) * kp * elem);
+	L.red = take((size_t) stream_reduce_width(NW, kp, elem) * kp * elem);
 	L.eth = take((size_t) kp * elem);
 	L.gam = take((size_t) kp * 8);
 	L.wsum = take((size_t) NW * 8);
-	L.xstage = take(C > 1 ? (size_t) 2 * kp * 8 : 0);             // [2] outgoing partial vector
-	L.xall = take(C > 1 ? (size_t) 2 * C * kp * 8 : 0);           // [2][C] incoming partial vectors
+	L.xstage = take(C > 1 ? (size_t) 2 * kp * elem : 0);          // [2] outgoing partial vector
+	L.xall = take(C > 1 ? (size_t) 2 * C * kp * elem : 0);        // [2][C] incoming partial vectors
 	L.wid = take((size_t) n_cap * 4);
 	L.cnt = take((size_t) n_cap * 4);
 	L.bar = take(32);
@@ -71,14 +77,15 @@ static inline int stream_nvec(int K, int elem) {
 
 // launch shape: (cluster size, warps per CTA).  TRLDA_STREAM_CLUSTER / TRLDA_STREAM_WARPS override.
 static void stream_shape(int elem, int* cluster, int* warps) {
-	int C = 2, NW = elem == 4 ? 8 : 4;
+	// measured at cfg-3 (fresh minibatch per step): one 16-warp CTA per document 70.8 ms/step, two 8-warp CTAs per SM
+	// 74.3, a 2-CTA cluster per document 102 (8 warps) — the cluster variants lose to their per-sweep exchange
+	int C = 1;
 	if(const char* e = getenv("TRLDA_STREAM_CLUSTER"))
-		C = atoi(e) == 1 ? 1 : (atoi(e) == 4 ? 4 : 2);
-	if(C == 1)
-		NW = 8;
+		C = atoi(e) == 2 ? 2 : (atoi(e) == 4 ? 4 : 1);
+	int NW = elem == 4 ? 16 : (C == 1 ? 8 : 4);
 	if(const char* e = getenv("TRLDA_STREAM_WARPS")) {
 		const int w = atoi(e);
-		if(w == 4 || w == 8 || (w == 16 && elem == 4 && C == 1))
+		if(w == 4 || w == 8 || (w == 16 && elem == 4))
 			NW = w;
 	}
 	if(elem == 8 && C > 1 && NW > 4)
@@ -119,21 +126,23 @@ __device__ __forceinline__ void s_mbar_wait(uint32_t bar, uint32_t parity) {
 
 template <typename T, int NW, int NVEC, int C>
 __global__ void __launch_bounds__(NW * 32, (C == 1 && NW == 4 ? 3 : (C == 1 && NW == 8 && sizeof(T) == 4 ? 2 : 1)))
-k_estep_stream(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, int64_t doc_offset, int n_cap) {
+k_estep_stream(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, int64_t doc_offset, int64_t count, int n_cap) {
 	extern __shared__ __align__(128) unsigned char smem[];
 	using V = typename SVec<T>::type;
 	constexpr int VN = SVec<T>::N;
 	constexpr int KP = NVEC * 32 * VN;                       // padded number of topic rows
 	constexpr int NT = NW * 32;
 	constexpr int TW = NW * C;                               // warps working on one document
+	constexpr int STREAM_DEPTH = stream_depth(C);
+	constexpr int RW = stream_reduce_width(NW, KP, (int) sizeof(T));
 	const StreamSmem L = stream_smem_layout(NW, C, KP, n_cap, (int) sizeof(T));
 	T* ring = reinterpret_cast<T*>(smem + L.ring);
 	T* red = reinterpret_cast<T*>(smem + L.red);
 	T* eth = reinterpret_cast<T*>(smem + L.eth);
 	double* gam = reinterpret_cast<double*>(smem + L.gam);
 	double* wsum = reinterpret_cast<double*>(smem + L.wsum);
-	double* xstage = reinterpret_cast<double*>(smem + L.xstage);
-	double* xall = reinterpret_cast<double*>(smem + L.xall);
+	T* xstage = reinterpret_cast<T*>(smem + L.xstage);
+	T* xall = reinterpret_cast<T*>(smem + L.xall);
 	int* wid = reinterpret_cast<int*>(smem + L.wid);
 	int* cnt = reinterpret_cast<int*>(smem + L.cnt);
 	uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.bar);
@@ -141,13 +150,9 @@ k_estep_stream(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, 
 	int rank = 0;
 	if(C > 1)
 		asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
-	const int64_t slot = doc_offset + blockIdx.x / C;
-	const int64_t d = order ? order[slot] : slot;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int gw = rank * NW + warp;                          // this warp's index among the document's warps
 	const int K = a.K;
-	const int64_t begin = docs.doc_ptr[d];
-	const int n = (int) (docs.doc_ptr[d + 1] - begin);
 	const T* __restrict__ beta = static_cast<const T*>(a.beta);
 
 	if(C > 1) {
@@ -161,6 +166,38 @@ k_estep_stream(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, 
 		asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
 	}
 
+	// this lane's rows: vectors v = 0..NVEC-1 cover rows (v * 32 + lane) * VN .. + VN
+	T* my_ring = ring + (size_t) warp * STREAM_DEPTH * KP;
+	const uint32_t ring_addr = s_smem_u32(my_ring);
+	// whole rounds of 32 vectors are moved, rows K..KP-1 of a column are the head of the next column (or the zeroed slack
+	// behind the matrix): finite values that meet etheta = 0 in the dot product and rows nobody reads in the sums
+	const uint32_t lane_bytes = (uint32_t) lane * 16u;
+	auto issue = [&](int j, int stage) {                           // gather column j into ring slot `stage`
+		const char* src = reinterpret_cast<const char*>(beta + (int64_t) wid[j] * K) + lane_bytes;
+		const uint32_t dst = ring_addr + (uint32_t) (stage * KP * (int) sizeof(T)) + lane_bytes;
+		#pragma unroll
+		for(int v = 0; v < NVEC; ++v)
+			asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + v * 512u), "l"(src + v * 512) : "memory");
+	};
+
+	const uint32_t xstage_addr = s_smem_u32(xstage), xall_addr = s_smem_u32(xall), bar_addr = s_smem_u32(bar);
+	constexpr uint32_t XBYTES = KP * sizeof(T);
+
+	int sweep = 0;         // counts the sweeps (= cluster exchanges) of all documents of this CTA
+	// debug phase timers (TRLDA_ESTEP_TICKS=1), thread 0's view: setup, stream, fold, exchange, update, test
+	const bool timing = a.ticks != nullptr && tid == 0;
+	long long tk[6] = {0, 0, 0, 0, 0, 0}, t_mark = 0;
+	long long docs_done = 0;
+	#define TRLDA_TICK(i) if(timing) { const long long now = clock64(); tk[i] += now - t_mark; t_mark = now; }
+	// persistent grid: the documents in flight (and with them the footprint of their tiles in L2) are set by the grid
+	for(int64_t item = blockIdx.x / C; item < count; item += gridDim.x / C) {
+	const int64_t slot = doc_offset + item;
+	const int64_t d = order ? order[slot] : slot;
+	const int64_t begin = docs.doc_ptr[d];
+	const int n = (int) (docs.doc_ptr[d + 1] - begin);
+	__syncthreads();       // the previous document's last reads of the shared vectors
+	if(timing)
+		t_mark = clock64();
 	for(int j = tid; j < n; j += NT) {
 		wid[j] = docs.word_ids[begin + j];
 		cnt[j] = docs.counts[begin + j];
@@ -176,25 +213,8 @@ k_estep_stream(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, 
 	}
 	__syncthreads();
 
-	// this lane's rows: vectors v = 0..NVEC-1 cover rows (v * 32 + lane) * VN .. + VN
-	T* my_ring = ring + (size_t) warp * STREAM_DEPTH * KP;
-	const uint32_t ring_addr = s_smem_u32(my_ring);
-	auto issue = [&](int j, int stage) {                           // gather column j into ring slot `stage`
-		const T* src = beta + (int64_t) wid[j] * K;
-		#pragma unroll
-		for(int v = 0; v < NVEC; ++v) {
-			const int row = (v * 32 + lane) * VN;
-			if(row < K)
-				asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
-					::"r"(ring_addr + (uint32_t) ((stage * KP + row) * sizeof(T))), "l"(src + row) : "memory");
-		}
-	};
-
-	const uint32_t xstage_addr = s_smem_u32(xstage), xall_addr = s_smem_u32(xall), bar_addr = s_smem_u32(bar);
-	constexpr uint32_t XBYTES = KP * 8;
-
+	TRLDA_TICK(0)
 	int it = 0;
-	int sweep = 0;
 	bool converged = false;
 	bool primed = false;   // the ring already holds the first columns of the coming sweep
 	int stage = 0;
@@ -230,27 +250,36 @@ k_estep_stream(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, 
 			__syncwarp();
 			const T* col = my_ring + (size_t) stage * KP;
 			T c[NVEC][VN];
-			double part = 0.0;
 			#pragma unroll
-			for(int v = 0; v < NVEC; ++v) {
-				const int row = (v * 32 + lane) * VN;
-				if(row < K) {
-					svec_get(*reinterpret_cast<const V*>(col + row), c[v]);
-				} else {
+			for(int v = 0; v < NVEC; ++v)
+				svec_get(*reinterpret_cast<const V*>(col + (v * 32 + lane) * VN), c[v]);
+			T wt;
+			if(sizeof(T) == 4) {
+				// mixed mode: four independent float chains per lane, float butterfly over the warp, float division
+				float part[4] = {0.f, 0.f, 0.f, 0.f};
+				#pragma unroll
+				for(int v = 0; v < NVEC; ++v)
 					#pragma unroll
 					for(int q = 0; q < VN; ++q)
-						c[v][q] = T(0);
-				}
-				// products of one 16-byte chunk are summed in T, chunks are added in float64
-				T chunk = e[v][0] * c[v][0];
+						part[q & 3] = fmaf((float) e[v][q], (float) c[v][q], part[q & 3]);
+				float phi = (part[0] + part[1]) + (part[2] + part[3]);
 				#pragma unroll
-				for(int q = 1; q < VN; ++q)
-					chunk = fma(e[v][q], c[v][q], chunk);
-				part += (double) chunk;
+				for(int o = 16; o > 0; o >>= 1)
+					phi += __shfl_xor_sync(0xffffffffu, phi, o);
+				wt = (T) ((float) cnt[j] / fmaxf(phi, 1e-37f));              // lda.cpp:183,192,199 (+1e-100 only matters at 0)
+			} else {
+				double part = 0.0;
+				#pragma unroll
+				for(int v = 0; v < NVEC; ++v) {
+					T chunk = e[v][0] * c[v][0];
+					#pragma unroll
+					for(int q = 1; q < VN; ++q)
+						chunk = fma(e[v][q], c[v][q], chunk);
+					part += (double) chunk;
+				}
+				const double phi = warp_sum(part) + 1e-100;                    // lda.cpp:183,199
+				wt = (T) ((double) cnt[j] / phi);                              // lda.cpp:192
 			}
-			const double phi = warp_sum(part) + 1e-100;                    // lda.cpp:183,199
-			const double w = (double) cnt[j] / phi;                        // lda.cpp:192
-			const T wt = (T) w;
 			#pragma unroll
 			for(int v = 0; v < NVEC; ++v)
 				#pragma unroll
@@ -271,30 +300,54 @@ k_estep_stream(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, 
 		if(!primed)
 			asm volatile("cp.async.wait_group 0;" ::: "memory");
 		// ---- the per-warp partial sums meet in shared memory, fixed order ------------------------------------------------
-		#pragma unroll
-		for(int v = 0; v < NVEC; ++v) {
-			V out;
-			T* o = reinterpret_cast<T*>(&out);
+		TRLDA_TICK(1)
+		auto store_acc = [&](int slot) {
 			#pragma unroll
-			for(int q = 0; q < VN; ++q)
-				o[q] = acc[v][q];
-			*reinterpret_cast<V*>(red + (size_t) warp * KP + (v * 32 + lane) * VN) = out;
+			for(int v = 0; v < NVEC; ++v) {
+				V out;
+				T* o = reinterpret_cast<T*>(&out);
+				#pragma unroll
+				for(int q = 0; q < VN; ++q)
+					o[q] = acc[v][q];
+				*reinterpret_cast<V*>(red + (size_t) slot * KP + (v * 32 + lane) * VN) = out;
+			}
+		};
+		if(RW < NW) {                                                  // upper half of the warps folds into the lower half
+			if(warp >= RW)
+				store_acc(warp - RW);
+			__syncthreads();
+			if(warp < RW) {
+				#pragma unroll
+				for(int v = 0; v < NVEC; ++v) {
+					T other[VN];
+					svec_get(*reinterpret_cast<const V*>(red + (size_t) warp * KP + (v * 32 + lane) * VN), other);
+					#pragma unroll
+					for(int q = 0; q < VN; ++q)
+						acc[v][q] += other[q];
+				}
+			}
+			__syncthreads();
+			if(warp < RW)
+				store_acc(warp);
+		} else {
+			store_acc(warp);
 		}
 		__syncthreads();
 
+		TRLDA_TICK(2)
 		const int buf = sweep & 1;
 		if(C > 1) {
 			// ---- cluster exchange: this CTA's partial K-vector goes to every CTA of the cluster (itself included) -------
 			if(tid == 0)
 				asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
 					::"r"(bar_addr + 8 * buf), "r"((uint32_t) C * XBYTES) : "memory");
-			double* out = xstage + (size_t) buf * KP;
+			T* out = xstage + (size_t) buf * KP;
 			for(int r = tid; r < KP; r += NT) {
 				double partial = 0.0;
 				#pragma unroll 4
-				for(int q = 0; q < NW; ++q)
+				for(int q = 0; q < RW; ++q)
 					partial += (double) red[(size_t) q * KP + r];
-				out[r] = partial;
+				out[r] = (T) partial;
 			}
 			__syncthreads();
 			if(sweep == 0)
@@ -310,16 +363,17 @@ k_estep_stream(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, 
 			s_mbar_wait(bar_addr + 8 * buf, (uint32_t) ((sweep >> 1) & 1));
 		}
 
+		TRLDA_TICK(3)
 		double delta_local = 0.0;
 		for(int r = tid; r < K; r += NT) {
 			double total = 0.0;
 			if(C > 1) {
 				#pragma unroll
 				for(int src = 0; src < C; ++src)
-					total += xall[(size_t) (buf * C + src) * KP + r];      // rank order: identical bits in every CTA
+					total += (double) xall[(size_t) (buf * C + src) * KP + r];   // rank order: identical bits in every CTA
 			} else {
 				#pragma unroll 4
-				for(int q = 0; q < NW; ++q)
+				for(int q = 0; q < RW; ++q)
 					total += (double) red[(size_t) q * KP + r];
 			}
 			const double eo = (double) eth[r];
@@ -341,6 +395,7 @@ k_estep_stream(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, 
 			}
 		}
 		++sweep;
+		TRLDA_TICK(4)
 		if(final_sweep)
 			break;
 		delta_local = warp_sum(delta_local);
@@ -352,10 +407,20 @@ k_estep_stream(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, 
 			delta += wsum[q];
 		++it;
 		converged = delta / K < a.threshold;                           // lda.cpp:202
-		__syncthreads();
+		// no second barrier: wsum and red are next written behind the barriers of the coming sweep's fold
+		TRLDA_TICK(5)
 	}
+	++docs_done;
 	if(rank == 0 && tid == 0 && a.iterations)
 		a.iterations[d] = it;
+	}
+	if(timing && rank == 0) {
+		for(int i = 0; i < 6; ++i)
+			atomicAdd(a.ticks + i, (unsigned long long) tk[i]);
+		atomicAdd(a.ticks + 14, (unsigned long long) sweep);
+		atomicAdd(a.ticks + 15, (unsigned long long) docs_done);
+	}
+	#undef TRLDA_TICK
 	if(C > 1) {
 		// nobody reads this CTA's staging buffers any more once every CTA has passed its last exchange
 		asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -363,12 +428,22 @@ k_estep_stream(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, 
 	}
 }
 
+// documents in flight: one CTA (cluster) per document, handed out by the hardware scheduler as SMs free up (a static
+// persistent grid measured 7 % slower: the documents of a CTA differ in sweeps).  TRLDA_STREAM_GRID = n runs a
+// persistent grid of n documents in flight instead (experiments on the L2 footprint of the tiles).
+static int64_t stream_grid_docs(int64_t count) {
+	if(const char* e = getenv("TRLDA_STREAM_GRID"))
+		if(atoi(e) > 0)
+			return std::min<int64_t>(count, atoi(e));
+	return count;
+}
+
 template <typename T, int NW, int NVEC, int C>
 static void launch_stream_t(const EStepArgs& args, const DeviceDocs& docs, const int32_t* order, int64_t offset,
                             int64_t count, int n_cap, size_t smem, cudaStream_t s) {
 	cudaFuncSetAttribute(k_estep_stream<T, NW, NVEC, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
 	cudaLaunchConfig_t cfg = {};
-	cfg.gridDim = dim3((unsigned) (count * C));
+	cfg.gridDim = dim3((unsigned) (stream_grid_docs(count) * C));
 	cfg.blockDim = dim3(NW * 32);
 	cfg.dynamicSmemBytes = smem;
 	cfg.stream = s;
@@ -379,7 +454,7 @@ static void launch_stream_t(const EStepArgs& args, const DeviceDocs& docs, const
 	attr[0].val.clusterDim.z = 1;
 	cfg.attrs = attr;
 	cfg.numAttrs = C > 1 ? 1 : 0;
-	cudaLaunchKernelEx(&cfg, k_estep_stream<T, NW, NVEC, C>, args, docs, order, offset, n_cap);
+	cudaLaunchKernelEx(&cfg, k_estep_stream<T, NW, NVEC, C>, args, docs, order, offset, count, n_cap);
 }
 
 template <typename T, int NW, int C>
@@ -409,8 +484,10 @@ void launch_estep_stream(const EStepArgs& args, const DeviceDocs& docs, const in
 #define TRLDA_STREAM_CASE(TYPE, WARPS, CLUSTER) \
 	if(NW == WARPS && C == CLUSTER) { launch_stream_v<TYPE, WARPS, CLUSTER>(nvec, args, docs, order, offset, count, n_cap, smem, s); return; }
 	if(elem_size == 4) {
+		TRLDA_STREAM_CASE(float, 16, 2)
 		TRLDA_STREAM_CASE(float, 8, 2)
 		TRLDA_STREAM_CASE(float, 4, 2)
+		TRLDA_STREAM_CASE(float, 16, 4)
 		TRLDA_STREAM_CASE(float, 8, 4)
 		TRLDA_STREAM_CASE(float, 4, 4)
 		TRLDA_STREAM_CASE(float, 8, 1)

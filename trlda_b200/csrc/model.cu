@@ -352,7 +352,14 @@ int ensure_beta(trlda_model* m) {
 		m->beta_elem = elem;
 		m->beta_valid = false;
 	}
-	CUDA_TRY(m, m->beta.ensure((size_t) m->K * m->V * elem));
+	// the streaming E-step reads whole 16-byte-vector rounds of a column (up to K rounded up to 32 vectors): the tail of
+	// the last column needs readable, finite bytes behind it
+	const size_t bytes = (size_t) m->K * m->V * elem, slack = 16384;
+	if(bytes + slack > m->beta.cap) {
+		CUDA_TRY(m, m->beta.ensure(bytes + slack));
+		CUDA_TRY(m, cudaMemsetAsync(static_cast<char*>(m->beta.p) + bytes, 0, m->beta.cap - bytes, m->stream));
+		m->beta_valid = false;
+	}
 	return TRLDA_OK;
 }
 
@@ -1480,11 +1487,16 @@ void trlda_destroy(trlda_model* m) {
 	if(m->ticks.p) {
 		unsigned long long t[16];
 		cudaMemcpy(t, m->ticks.p, sizeof(t), cudaMemcpyDeviceToHost);
-		static const char* names[10] = {"stage+gather issue+psi0", "gather wait", "initial pass2+push", "initial exchange+W",
-		                                "pass1", "gamma/psi/delta", "pass2+push", "exchange+W", "results+doc_stat", "-"};
-		fprintf(stderr, "[trlda] fast E-step phase timers: %llu documents, %llu inner iterations\n", t[15], t[14]);
-		for(int i = 0; i < 10; ++i)
-			fprintf(stderr, "[trlda]   %-26s %10.0f cycles/doc\n", names[i], t[15] ? (double) t[i] / (double) t[15] : 0.0);
+		static const char* fast_names[10] = {"stage+gather issue+psi0", "gather wait", "initial pass2+push", "initial exchange+W",
+		                                     "pass1", "gamma/psi/delta", "pass2+push", "exchange+W", "results+doc_stat", "-"};
+		static const char* stream_names[10] = {"document setup", "sweep (stream columns)", "fold partial sums", "cluster exchange",
+		                                       "gamma/psi update + results", "convergence test", "-", "-", "-", "-"};
+		const bool streamed = m->stream_mode != 0;
+		fprintf(stderr, "[trlda] %s E-step phase timers: %llu documents, %llu %s\n", streamed ? "streaming" : "fast", t[15], t[14],
+		        streamed ? "sweeps" : "inner iterations");
+		for(int i = 0; i < (streamed ? 6 : 10); ++i)
+			fprintf(stderr, "[trlda]   %-26s %10.0f cycles/doc\n", (streamed ? stream_names : fast_names)[i],
+			        t[15] ? (double) t[i] / (double) t[15] : 0.0);
 		m->ticks.release();
 	}
 	for(void* p : m->peer_opened)
