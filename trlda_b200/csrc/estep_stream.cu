@@ -37,8 +37,6 @@ template <> struct SVec<double> { using type = double2; static constexpr int N =
 __device__ __forceinline__ void svec_get(const float4& v, float (&o)[4]) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
 __device__ __forceinline__ void svec_get(const double2& v, double (&o)[2]) { o[0] = v.x; o[1] = v.y; }
 
-// columns in flight per warp: a cluster CTA has fewer columns per warp and reads them from L2, it needs a deeper ring
-__host__ __device__ constexpr int stream_depth(int C) { return 2; }
 
 // how many per-warp partial vectors meet in shared memory at once: above 32 KB the warps fold pairwise first
 __host__ __device__ constexpr int stream_reduce_width(int NW, int kp, int elem) {
@@ -46,14 +44,14 @@ __host__ __device__ constexpr int stream_reduce_width(int NW, int kp, int elem) 
 }
 
 struct StreamSmem {
-	size_t ring, red, eth, gam, wsum, xstage, xall, wid, cnt, bar, total;
+	size_t ring, red, eth, gam, wsum, xstage, xall, wid, cnt, bar, rbar, total;
 };
 
-__host__ __device__ inline StreamSmem stream_smem_layout(int NW, int C, int kp, int n_cap, int elem) {
+__host__ __device__ inline StreamSmem stream_smem_layout(int NW, int C, int depth, int kp, int n_cap, int elem) {
 	StreamSmem L;
 	size_t o = 0;
 	auto take = [&o](size_t bytes) { size_t at = o; o += (bytes + 15) & ~size_t(15); return at; };
-	L.ring = take((size_t) NW * stream_depth(C) * kp * elem);
+	L.ring = take((size_t) NW * depth * kp * elem);
 	L.red = take((size_t) stream_reduce_width(NW, kp, elem) * kp * elem);
 	L.eth = take((size_t) kp * elem);
 	L.gam = take((size_t) kp * 8);
@@ -63,6 +61,7 @@ __host__ __device__ inline StreamSmem stream_smem_layout(int NW, int C, int kp, 
 	L.wid = take((size_t) n_cap * 4);
 	L.cnt = take((size_t) n_cap * 4);
 	L.bar = take(32);
+	L.rbar = take((size_t) NW * depth * 8);                // one mbarrier per ring slot (bulk-copy variant)
 	L.total = o;
 	return L;
 }
@@ -75,23 +74,25 @@ static inline int stream_nvec(int K, int elem) {
 	return nvec;
 }
 
-// launch shape: (cluster size, warps per CTA).  TRLDA_STREAM_CLUSTER / TRLDA_STREAM_WARPS override.
-static void stream_shape(int elem, int* cluster, int* warps) {
-	// measured at cfg-3 (fresh minibatch per step): one 16-warp CTA per document 70.8 ms/step, two 8-warp CTAs per SM
-	// 74.3, a 2-CTA cluster per document 102 (8 warps) — the cluster variants lose to their per-sweep exchange
-	int C = 1;
-	if(const char* e = getenv("TRLDA_STREAM_CLUSTER"))
-		C = atoi(e) == 2 ? 2 : (atoi(e) == 4 ? 4 : 1);
-	int NW = elem == 4 ? 16 : (C == 1 ? 8 : 4);
-	if(const char* e = getenv("TRLDA_STREAM_WARPS")) {
-		const int w = atoi(e);
-		if(w == 4 || w == 8 || (w == 16 && elem == 4))
-			NW = w;
-	}
-	if(elem == 8 && C > 1 && NW > 4)
-		NW = 4;
-	*cluster = C;
-	*warps = NW;
+// launch shape: cluster size, warps per CTA, ring slots per warp.  Measured at cfg-3 (fresh minibatch per step):
+// clusters lose to their per-sweep exchange (2 x 8 warps: 102 ms/step against 74); with the bulk-copy ring the E-step
+// takes 56.9 ms/step with 16 warps x 2 slots, 59.5 with 12 x 3, 60.3 with 12 x 2, 75.1 with 8 x 4: warps, not slots.
+// TRLDA_STREAM_CLUSTER / TRLDA_STREAM_WARPS / TRLDA_STREAM_DEPTH override (only compiled combinations are accepted).
+struct StreamShape { int C, NW, D; };
+static const StreamShape kFloatShapes[] = {{1, 16, 2}, {1, 12, 3}, {1, 12, 2}, {1, 8, 4}, {1, 8, 2}, {1, 4, 2}, {2, 8, 2}};
+static const StreamShape kDoubleShapes[] = {{1, 8, 2}, {1, 4, 2}, {1, 4, 4}, {2, 4, 2}};
+
+static StreamShape stream_shape(int elem) {
+	const StreamShape* shapes = elem == 4 ? kFloatShapes : kDoubleShapes;
+	const int count = elem == 4 ? (int) (sizeof(kFloatShapes) / sizeof(StreamShape)) : (int) (sizeof(kDoubleShapes) / sizeof(StreamShape));
+	const char* ec = getenv("TRLDA_STREAM_CLUSTER");
+	const char* ew = getenv("TRLDA_STREAM_WARPS");
+	const char* ed = getenv("TRLDA_STREAM_DEPTH");
+	const int C = ec ? atoi(ec) : 0, NW = ew ? atoi(ew) : 0, D = ed ? atoi(ed) : 0;
+	for(int i = 0; i < count; ++i)
+		if((!C || shapes[i].C == C) && (!NW || shapes[i].NW == NW) && (!D || shapes[i].D == D))
+			return shapes[i];
+	return shapes[0];
 }
 
 // applicable?  (aligned columns, K small enough for the per-lane register tile, everything fits in shared memory)
@@ -103,9 +104,8 @@ bool stream_estep_applicable(int K, int n_max, int elem, int smem_optin) {
 		return false;
 	const int kp = nvec * 32 * (16 / elem);
 	const int n_cap = std::max(32, (n_max + 31) / 32 * 32);
-	int C, NW;
-	stream_shape(elem, &C, &NW);
-	return stream_smem_layout(NW, C, kp, n_cap, elem).total <= (size_t) smem_optin - 1024;
+	const StreamShape sh = stream_shape(elem);
+	return stream_smem_layout(sh.NW, sh.C, sh.D, kp, n_cap, elem).total <= (size_t) smem_optin - 1024;
 }
 
 __device__ __forceinline__ uint32_t s_smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
@@ -124,7 +124,7 @@ __device__ __forceinline__ void s_mbar_wait(uint32_t bar, uint32_t parity) {
 			: "=r"(done) : "r"(bar), "r"(parity) : "memory");
 }
 
-template <typename T, int NW, int NVEC, int C>
+template <typename T, int NW, int NVEC, int C, bool BULK, int STREAM_DEPTH>
 __global__ void __launch_bounds__(NW * 32, (C == 1 && NW == 4 ? 3 : (C == 1 && NW == 8 && sizeof(T) == 4 ? 2 : 1)))
 k_estep_stream(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, int64_t doc_offset, int64_t count, int n_cap) {
 	extern __shared__ __align__(128) unsigned char smem[];
@@ -133,9 +133,8 @@ k_estep_stream(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, 
 	constexpr int KP = NVEC * 32 * VN;                       // padded number of topic rows
 	constexpr int NT = NW * 32;
 	constexpr int TW = NW * C;                               // warps working on one document
-	constexpr int STREAM_DEPTH = stream_depth(C);
 	constexpr int RW = stream_reduce_width(NW, KP, (int) sizeof(T));
-	const StreamSmem L = stream_smem_layout(NW, C, KP, n_cap, (int) sizeof(T));
+	const StreamSmem L = stream_smem_layout(NW, C, STREAM_DEPTH, KP, n_cap, (int) sizeof(T));
 	T* ring = reinterpret_cast<T*>(smem + L.ring);
 	T* red = reinterpret_cast<T*>(smem + L.red);
 	T* eth = reinterpret_cast<T*>(smem + L.eth);
@@ -146,6 +145,7 @@ k_estep_stream(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, 
 	int* wid = reinterpret_cast<int*>(smem + L.wid);
 	int* cnt = reinterpret_cast<int*>(smem + L.cnt);
 	uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.bar);
+	uint64_t* rbar = reinterpret_cast<uint64_t*>(smem + L.rbar);
 
 	int rank = 0;
 	if(C > 1)
@@ -172,13 +172,53 @@ k_estep_stream(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, 
 	// whole rounds of 32 vectors are moved, rows K..KP-1 of a column are the head of the next column (or the zeroed slack
 	// behind the matrix): finite values that meet etheta = 0 in the dot product and rows nobody reads in the sums
 	const uint32_t lane_bytes = (uint32_t) lane * 16u;
+	const uint32_t rbar_addr = s_smem_u32(rbar + (size_t) warp * STREAM_DEPTH);
+	const uint32_t col_bytes = (uint32_t) K * (uint32_t) sizeof(T);
+	uint32_t phases = 0;                                           // bulk variant: parity of the next completion per slot
 	auto issue = [&](int j, int stage) {                           // gather column j into ring slot `stage`
-		const char* src = reinterpret_cast<const char*>(beta + (int64_t) wid[j] * K) + lane_bytes;
-		const uint32_t dst = ring_addr + (uint32_t) (stage * KP * (int) sizeof(T)) + lane_bytes;
-		#pragma unroll
-		for(int v = 0; v < NVEC; ++v)
-			asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + v * 512u), "l"(src + v * 512) : "memory");
+		if(BULK) {
+			// one bulk copy of the K values per column, issued by one lane, written by the copy engine: the load/store
+			// pipe only sees the LDS that read the column back (LDGSTS costs it 8 cycles per 512 bytes, LDS.128 4)
+			if(lane == 0) {
+				const T* src = beta + (int64_t) wid[j] * K;
+				const uint32_t dst = ring_addr + (uint32_t) (stage * KP * (int) sizeof(T));
+				const uint32_t mb = rbar_addr + 8u * (uint32_t) stage;
+				asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(col_bytes) : "memory");
+				asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+					::"r"(dst), "l"(src), "r"(col_bytes), "r"(mb) : "memory");
+			}
+		} else {
+			const char* src = reinterpret_cast<const char*>(beta + (int64_t) wid[j] * K) + lane_bytes;
+			const uint32_t dst = ring_addr + (uint32_t) (stage * KP * (int) sizeof(T)) + lane_bytes;
+			#pragma unroll
+			for(int v = 0; v < NVEC; ++v)
+				asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + v * 512u), "l"(src + v * 512) : "memory");
+		}
 	};
+	auto commit = [&]() {
+		if(!BULK)
+			asm volatile("cp.async.commit_group;" ::: "memory");
+	};
+	auto wait_slot = [&](int stage) {
+		if(BULK) {
+			s_mbar_wait(rbar_addr + 8u * (uint32_t) stage, (phases >> stage) & 1u);
+			phases ^= 1u << stage;
+		} else {
+			asm volatile("cp.async.wait_group %0;" ::"n"(STREAM_DEPTH - 1) : "memory");
+		}
+	};
+	if(BULK) {
+		// the copies move K values, the lanes read KP: the tail of every slot is zeroed once
+		for(int i = tid; i < NW * STREAM_DEPTH * (KP - K); i += NT)
+			ring[(size_t) (i / (KP - K)) * KP + K + i % (KP - K)] = T(0);
+		if(lane == 0) {
+			for(int st = 0; st < STREAM_DEPTH; ++st)
+				asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(rbar_addr + 8u * (uint32_t) st));
+			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		}
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+		__syncthreads();
+	}
 
 	const uint32_t xstage_addr = s_smem_u32(xstage), xall_addr = s_smem_u32(xall), bar_addr = s_smem_u32(bar);
 	constexpr uint32_t XBYTES = KP * sizeof(T);
@@ -236,7 +276,7 @@ k_estep_stream(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, 
 			for(int s = 0; s < STREAM_DEPTH; ++s) {
 				if(s < M)
 					issue(gw + s * TW, s);
-				asm volatile("cp.async.commit_group;" ::: "memory");
+				commit();
 			}
 			stage = 0;
 		}
@@ -246,7 +286,7 @@ k_estep_stream(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, 
 		const bool prime_next = !final_sweep && M >= STREAM_DEPTH;
 		for(int mcol = 0; mcol < M; ++mcol) {
 			const int j = gw + mcol * TW;
-			asm volatile("cp.async.wait_group %0;" ::"n"(STREAM_DEPTH - 1) : "memory");
+			wait_slot(stage);
 			__syncwarp();
 			const T* col = my_ring + (size_t) stage * KP;
 			T c[NVEC][VN];
@@ -293,11 +333,11 @@ k_estep_stream(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, 
 				issue(gw + mn * TW, stage);
 			else if(prime_next)
 				issue(gw + (mn - M) * TW, stage);
-			asm volatile("cp.async.commit_group;" ::: "memory");
+			commit();
 			stage = stage + 1 == STREAM_DEPTH ? 0 : stage + 1;
 		}
 		primed = prime_next;
-		if(!primed)
+		if(!primed && !BULK)
 			asm volatile("cp.async.wait_group 0;" ::: "memory");
 		// ---- the per-warp partial sums meet in shared memory, fixed order ------------------------------------------------
 		TRLDA_TICK(1)
@@ -438,10 +478,11 @@ static int64_t stream_grid_docs(int64_t count) {
 	return count;
 }
 
-template <typename T, int NW, int NVEC, int C>
-static void launch_stream_t(const EStepArgs& args, const DeviceDocs& docs, const int32_t* order, int64_t offset,
+template <typename T, int NW, int NVEC, int C, bool BULK, int DEPTH>
+static void launch_stream_b(const EStepArgs& args, const DeviceDocs& docs, const int32_t* order, int64_t offset,
                             int64_t count, int n_cap, size_t smem, cudaStream_t s) {
-	cudaFuncSetAttribute(k_estep_stream<T, NW, NVEC, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+	auto kernel = k_estep_stream<T, NW, NVEC, C, BULK, DEPTH>;
+	cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
 	cudaLaunchConfig_t cfg = {};
 	cfg.gridDim = dim3((unsigned) (stream_grid_docs(count) * C));
 	cfg.blockDim = dim3(NW * 32);
@@ -454,19 +495,35 @@ static void launch_stream_t(const EStepArgs& args, const DeviceDocs& docs, const
 	attr[0].val.clusterDim.z = 1;
 	cfg.attrs = attr;
 	cfg.numAttrs = C > 1 ? 1 : 0;
-	cudaLaunchKernelEx(&cfg, k_estep_stream<T, NW, NVEC, C>, args, docs, order, offset, count, n_cap);
+	cudaLaunchKernelEx(&cfg, kernel, args, docs, order, offset, count, n_cap);
 }
 
-template <typename T, int NW, int C>
+// columns travel by cp.async.bulk (one copy per column, written by the copy engine); TRLDA_STREAM_BULK = 0 goes back to
+// 16-byte cp.async (LDGSTS), which costs the load/store pipe 8 cycles per 512 bytes: 63.8 against 56.9 ms/step of E-step
+static bool stream_bulk() {
+	static const bool on = [] { const char* e = getenv("TRLDA_STREAM_BULK"); return !e || atoi(e) != 0; }();
+	return on;
+}
+
+template <typename T, int NW, int NVEC, int C, int DEPTH>
+static void launch_stream_t(const EStepArgs& args, const DeviceDocs& docs, const int32_t* order, int64_t offset,
+                            int64_t count, int n_cap, size_t smem, cudaStream_t s) {
+	if(C == 1 && stream_bulk())
+		launch_stream_b<T, NW, NVEC, 1, true, DEPTH>(args, docs, order, offset, count, n_cap, smem, s);
+	else
+		launch_stream_b<T, NW, NVEC, C, false, DEPTH>(args, docs, order, offset, count, n_cap, smem, s);
+}
+
+template <typename T, int NW, int C, int DEPTH>
 static void launch_stream_v(int nvec, const EStepArgs& args, const DeviceDocs& docs, const int32_t* order, int64_t offset,
                             int64_t count, int n_cap, size_t smem, cudaStream_t s) {
 	constexpr int MAXV = sizeof(T) == 4 ? 8 : 16;
 	switch(nvec) {
-		case 1: launch_stream_t<T, NW, 1, C>(args, docs, order, offset, count, n_cap, smem, s); break;
-		case 2: launch_stream_t<T, NW, 2, C>(args, docs, order, offset, count, n_cap, smem, s); break;
-		case 4: launch_stream_t<T, NW, 4, C>(args, docs, order, offset, count, n_cap, smem, s); break;
-		case 8: launch_stream_t<T, NW, 8, C>(args, docs, order, offset, count, n_cap, smem, s); break;
-		default: launch_stream_t<T, NW, MAXV, C>(args, docs, order, offset, count, n_cap, smem, s); break;
+		case 1: launch_stream_t<T, NW, 1, C, DEPTH>(args, docs, order, offset, count, n_cap, smem, s); break;
+		case 2: launch_stream_t<T, NW, 2, C, DEPTH>(args, docs, order, offset, count, n_cap, smem, s); break;
+		case 4: launch_stream_t<T, NW, 4, C, DEPTH>(args, docs, order, offset, count, n_cap, smem, s); break;
+		case 8: launch_stream_t<T, NW, 8, C, DEPTH>(args, docs, order, offset, count, n_cap, smem, s); break;
+		default: launch_stream_t<T, NW, MAXV, C, DEPTH>(args, docs, order, offset, count, n_cap, smem, s); break;
 	}
 }
 
@@ -475,29 +532,27 @@ void launch_estep_stream(const EStepArgs& args, const DeviceDocs& docs, const in
 	(void) cold;
 	if(count == 0)
 		return;
-	int C, NW;
-	stream_shape(elem_size, &C, &NW);
+	const StreamShape sh = stream_shape(elem_size);
 	const int nvec = stream_nvec(args.K, elem_size);
 	const int n_cap = std::max(32, (n_max + 31) / 32 * 32);
 	const int kp = nvec * 32 * (16 / elem_size);
-	const size_t smem = stream_smem_layout(NW, C, kp, n_cap, elem_size).total;
-#define TRLDA_STREAM_CASE(TYPE, WARPS, CLUSTER) \
-	if(NW == WARPS && C == CLUSTER) { launch_stream_v<TYPE, WARPS, CLUSTER>(nvec, args, docs, order, offset, count, n_cap, smem, s); return; }
-	if(elem_size == 4) {
-		TRLDA_STREAM_CASE(float, 16, 2)
-		TRLDA_STREAM_CASE(float, 8, 2)
-		TRLDA_STREAM_CASE(float, 4, 2)
-		TRLDA_STREAM_CASE(float, 16, 4)
-		TRLDA_STREAM_CASE(float, 8, 4)
-		TRLDA_STREAM_CASE(float, 4, 4)
-		TRLDA_STREAM_CASE(float, 8, 1)
-		TRLDA_STREAM_CASE(float, 4, 1)
-		TRLDA_STREAM_CASE(float, 16, 1)
+	const size_t smem = stream_smem_layout(sh.NW, sh.C, sh.D, kp, n_cap, elem_size).total;
+#define TRLDA_STREAM_CASE(TYPE, CLUSTER, WARPS, DEPTH) \
+	if(sh.C == CLUSTER && sh.NW == WARPS && sh.D == DEPTH) { \
+		launch_stream_v<TYPE, WARPS, CLUSTER, DEPTH>(nvec, args, docs, order, offset, count, n_cap, smem, s); return; }
+	if(elem_size == 4) {                                  // keep in step with kFloatShapes / kDoubleShapes
+		TRLDA_STREAM_CASE(float, 1, 12, 3)
+		TRLDA_STREAM_CASE(float, 1, 16, 2)
+		TRLDA_STREAM_CASE(float, 1, 12, 2)
+		TRLDA_STREAM_CASE(float, 1, 8, 4)
+		TRLDA_STREAM_CASE(float, 1, 8, 2)
+		TRLDA_STREAM_CASE(float, 1, 4, 2)
+		TRLDA_STREAM_CASE(float, 2, 8, 2)
 	} else {
-		TRLDA_STREAM_CASE(double, 4, 2)
-		TRLDA_STREAM_CASE(double, 4, 4)
-		TRLDA_STREAM_CASE(double, 8, 1)
-		TRLDA_STREAM_CASE(double, 4, 1)
+		TRLDA_STREAM_CASE(double, 1, 8, 2)
+		TRLDA_STREAM_CASE(double, 1, 4, 2)
+		TRLDA_STREAM_CASE(double, 1, 4, 4)
+		TRLDA_STREAM_CASE(double, 2, 4, 2)
 	}
 #undef TRLDA_STREAM_CASE
 }
