@@ -82,7 +82,7 @@ struct StreamShape { int C, NW, D; };
 static const StreamShape kFloatShapes[] = {{1, 16, 2}, {1, 12, 3}, {1, 12, 2}, {1, 8, 4}, {1, 8, 2}, {1, 4, 2}, {2, 8, 2}};
 static const StreamShape kDoubleShapes[] = {{1, 8, 2}, {1, 4, 2}, {1, 4, 4}, {2, 4, 2}};
 
-static StreamShape stream_shape(int elem) {
+static StreamShape stream_shape(int elem, int K) {
 	const StreamShape* shapes = elem == 4 ? kFloatShapes : kDoubleShapes;
 	const int count = elem == 4 ? (int) (sizeof(kFloatShapes) / sizeof(StreamShape)) : (int) (sizeof(kDoubleShapes) / sizeof(StreamShape));
 	const char* ec = getenv("TRLDA_STREAM_CLUSTER");
@@ -91,7 +91,7 @@ static StreamShape stream_shape(int elem) {
 	const int C = ec ? atoi(ec) : 0, NW = ew ? atoi(ew) : 0, D = ed ? atoi(ed) : 0;
 	for(int i = 0; i < count; ++i)
 		if((!C || shapes[i].C == C) && (!NW || shapes[i].NW == NW) && (!D || shapes[i].D == D))
-			return shapes[i];
+			return (C || NW || D) ? shapes[i] : (elem == 4 && K * elem < 2048 ? StreamShape{1, 8, 2} : shapes[i]);
 	return shapes[0];
 }
 
@@ -104,7 +104,7 @@ bool stream_estep_applicable(int K, int n_max, int elem, int smem_optin) {
 		return false;
 	const int kp = nvec * 32 * (16 / elem);
 	const int n_cap = std::max(32, (n_max + 31) / 32 * 32);
-	const StreamShape sh = stream_shape(elem);
+	const StreamShape sh = stream_shape(elem, K);
 	return stream_smem_layout(sh.NW, sh.C, sh.D, kp, n_cap, elem).total <= (size_t) smem_optin - 1024;
 }
 
@@ -169,10 +169,10 @@ k_estep_stream(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, 
 	// this lane's rows: vectors v = 0..NVEC-1 cover rows (v * 32 + lane) * VN .. + VN
 	T* my_ring = ring + (size_t) warp * STREAM_DEPTH * KP;
 	const uint32_t ring_addr = s_smem_u32(my_ring);
+	const uint32_t rbar_addr = s_smem_u32(rbar + (size_t) warp * STREAM_DEPTH);
 	// whole rounds of 32 vectors are moved, rows K..KP-1 of a column are the head of the next column (or the zeroed slack
 	// behind the matrix): finite values that meet etheta = 0 in the dot product and rows nobody reads in the sums
 	const uint32_t lane_bytes = (uint32_t) lane * 16u;
-	const uint32_t rbar_addr = s_smem_u32(rbar + (size_t) warp * STREAM_DEPTH);
 	const uint32_t col_bytes = (uint32_t) K * (uint32_t) sizeof(T);
 	uint32_t phases = 0;                                           // bulk variant: parity of the next completion per slot
 	auto issue = [&](int j, int stage) {                           // gather column j into ring slot `stage`
@@ -184,7 +184,7 @@ k_estep_stream(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, 
 				const uint32_t dst = ring_addr + (uint32_t) (stage * KP * (int) sizeof(T));
 				const uint32_t mb = rbar_addr + 8u * (uint32_t) stage;
 				asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(col_bytes) : "memory");
-				asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+				asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
 					::"r"(dst), "l"(src), "r"(col_bytes), "r"(mb) : "memory");
 			}
 		} else {
@@ -306,7 +306,7 @@ k_estep_stream(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, 
 				#pragma unroll
 				for(int o = 16; o > 0; o >>= 1)
 					phi += __shfl_xor_sync(0xffffffffu, phi, o);
-				wt = (T) ((float) cnt[j] / fmaxf(phi, 1e-37f));              // lda.cpp:183,192,199 (+1e-100 only matters at 0)
+				wt = (T) __fdividef((float) cnt[j], fmaxf(phi, 1e-37f));     // lda.cpp:183,192,199 (+1e-100 only matters at 0)
 			} else {
 				double part = 0.0;
 				#pragma unroll
@@ -500,15 +500,17 @@ static void launch_stream_b(const EStepArgs& args, const DeviceDocs& docs, const
 
 // columns travel by cp.async.bulk (one copy per column, written by the copy engine); TRLDA_STREAM_BULK = 0 goes back to
 // 16-byte cp.async (LDGSTS), which costs the load/store pipe 8 cycles per 512 bytes: 63.8 against 56.9 ms/step of E-step
-static bool stream_bulk() {
-	static const bool on = [] { const char* e = getenv("TRLDA_STREAM_BULK"); return !e || atoi(e) != 0; }();
-	return on;
+// Short columns (K = 100 or 200: 400-1600 bytes) stay with cp.async, the per-copy cost of the bulk path does not pay:
+// cfg-5 (K = 200) 117 ms per batch with bulk copies and one 16-warp CTA per SM against 33 ms with two 8-warp CTAs.
+static bool stream_bulk(int column_bytes) {
+	static const int mode = [] { const char* e = getenv("TRLDA_STREAM_BULK"); return e ? (atoi(e) != 0 ? 1 : 0) : -1; }();
+	return mode < 0 ? column_bytes >= 2048 : mode == 1;
 }
 
 template <typename T, int NW, int NVEC, int C, int DEPTH>
 static void launch_stream_t(const EStepArgs& args, const DeviceDocs& docs, const int32_t* order, int64_t offset,
                             int64_t count, int n_cap, size_t smem, cudaStream_t s) {
-	if(C == 1 && stream_bulk())
+	if(C == 1 && stream_bulk(args.K * (int) sizeof(T)))
 		launch_stream_b<T, NW, NVEC, 1, true, DEPTH>(args, docs, order, offset, count, n_cap, smem, s);
 	else
 		launch_stream_b<T, NW, NVEC, C, false, DEPTH>(args, docs, order, offset, count, n_cap, smem, s);
@@ -532,7 +534,7 @@ void launch_estep_stream(const EStepArgs& args, const DeviceDocs& docs, const in
 	(void) cold;
 	if(count == 0)
 		return;
-	const StreamShape sh = stream_shape(elem_size);
+	const StreamShape sh = stream_shape(elem_size, args.K);
 	const int nvec = stream_nvec(args.K, elem_size);
 	const int n_cap = std::max(32, (n_max + 31) / 32 * 32);
 	const int kp = nvec * 32 * (16 / elem_size);
