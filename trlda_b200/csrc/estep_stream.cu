@@ -242,14 +242,25 @@ k_estep_stream(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, 
 		wid[j] = docs.word_ids[begin + j];
 		cnt[j] = docs.counts[begin + j];
 	}
-	for(int r = tid; r < KP; r += NT) {
-		double g = 0.0, e = 0.0;
-		if(r < K) {
-			g = a.gamma[d * K + r];
-			e = exp_digamma_for<T>(g, 0.0);                       // lda.cpp:174
+	for(int r0 = tid; r0 < KP; r0 += 2 * NT) {                      // two rows per trip: their psi/exp chains overlap
+		double g[2];
+		T e[2];
+		#pragma unroll
+		for(int u = 0; u < 2; ++u) {
+			const int r = r0 + u * NT;
+			g[u] = r < K ? a.gamma[d * K + r] : 1.0;
 		}
-		gam[r] = g;
-		eth[r] = (T) e;
+		#pragma unroll
+		for(int u = 0; u < 2; ++u)
+			e[u] = (T) exp_digamma_for<T>(g[u], 0.0);             // lda.cpp:174
+		#pragma unroll
+		for(int u = 0; u < 2; ++u) {
+			const int r = r0 + u * NT;
+			if(r < KP) {
+				gam[r] = r < K ? g[u] : 0.0;
+				eth[r] = r < K ? e[u] : T(0);
+			}
+		}
 	}
 	__syncthreads();
 
@@ -405,33 +416,61 @@ k_estep_stream(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, 
 
 		TRLDA_TICK(3)
 		double delta_local = 0.0;
-		for(int r = tid; r < K; r += NT) {
-			double total = 0.0;
-			if(C > 1) {
-				#pragma unroll
-				for(int src = 0; src < C; ++src)
-					total += (double) xall[(size_t) (buf * C + src) * KP + r];   // rank order: identical bits in every CTA
-			} else {
-				#pragma unroll 4
-				for(int q = 0; q < RW; ++q)
-					total += (double) red[(size_t) q * KP + r];
+		// two rows per thread and trip, so that their chains (sum of the partials, psi, exp) overlap
+		for(int r0 = tid; r0 < K; r0 += 2 * NT) {
+			double total[2], eo[2];
+			int row[2];
+			bool live[2];
+			#pragma unroll
+			for(int u = 0; u < 2; ++u) {
+				live[u] = r0 + u * NT < K;
+				row[u] = live[u] ? r0 + u * NT : r0;
+				const int r = row[u];
+				total[u] = 0.0;
+				if(C > 1) {
+					#pragma unroll
+					for(int src = 0; src < C; ++src)
+						total[u] += (double) xall[(size_t) (buf * C + src) * KP + r];   // rank order: identical bits in every CTA
+				} else {
+					#pragma unroll
+					for(int q = 0; q < RW; ++q)
+						total[u] += (double) red[(size_t) q * KP + r];
+				}
+				eo[u] = (double) eth[r];
 			}
-			const double eo = (double) eth[r];
 			if(final_sweep) {
-				if(C == 1 || r % C == rank) {                          // the CTAs share the output rows
-					a.doc_stat[d * K + r] = total * eo;
-					a.gamma[d * K + r] = gam[r];
-					a.etheta[d * K + r] = eo;
-					if(a.etheta32)
-						a.etheta32[d * K + r] = (float) eo;
+				#pragma unroll
+				for(int u = 0; u < 2; ++u) {
+					const int r = row[u];
+					if(live[u] && (C == 1 || r % C == rank)) {             // the CTAs share the output rows
+						a.doc_stat[d * K + r] = total[u] * eo[u];
+						a.gamma[d * K + r] = gam[r];
+						a.etheta[d * K + r] = eo[u];
+						if(a.etheta32)
+							a.etheta32[d * K + r] = (float) eo[u];
+					}
 				}
 			} else {                                                   // lda.cpp:186-197
-				const double g_old = gam[r];
-				double g_new = total * eo;
-				g_new += a.alpha[r];
-				delta_local += fabs(g_old - g_new);
-				gam[r] = g_new;
-				eth[r] = (T) exp_digamma_for<T>(g_new, 0.0);
+				double g_new[2];
+				T e_new[2];
+				#pragma unroll
+				for(int u = 0; u < 2; ++u) {
+					g_new[u] = total[u] * eo[u];
+					g_new[u] += a.alpha[row[u]];
+				}
+				#pragma unroll
+				for(int u = 0; u < 2; ++u)
+					e_new[u] = (T) exp_digamma_for<T>(g_new[u], 0.0);     // fp64 also in mixed mode: a float32 evaluation
+					                                                      // (5e-7) pushed lambda past the 1e-4 bound of the mode
+				#pragma unroll
+				for(int u = 0; u < 2; ++u) {
+					if(live[u]) {
+						const int r = row[u];
+						delta_local += fabs(gam[r] - g_new[u]);
+						gam[r] = g_new[u];
+						eth[r] = e_new[u];
+					}
+				}
 			}
 		}
 		++sweep;

@@ -148,6 +148,7 @@ template <typename T> __device__ __forceinline__ double exp_digamma_for(double x
 template <> __device__ __forceinline__ double exp_digamma_for<double>(double x, double c) { return exp_digamma_shifted(x, c); }
 template <> __device__ __forceinline__ double exp_digamma_for<float>(double x, double c) { return exp_digamma_shifted_mixed(x, c); }
 
+
 // psi'(x) = zeta(2, x) for x > 0: shift to s >= 10 by the recurrence psi'(x) = psi'(x+1) + 1/x^2, then the
 // asymptotic series 1/s + 1/(2 s^2) + sum B_2k / s^(2k+1).  Only K+1 values per alpha update are needed
 // (onlinelda.cpp:132-133), so clarity beats speed here.
