@@ -20,6 +20,16 @@ def models():
 	return trlda.models
 
 
+@pytest.fixture(autouse=True)
+def _fixed_seeds():
+	"""the reference's directional tests (empirical Bayes, lower bound) draw their corpora with `sample()`; unseeded they
+	fail once in a while by chance, which says nothing about the code under test"""
+	import trlda
+	np.random.seed(20261017)
+	trlda.seed(20261017)
+	yield
+
+
 def test_basics(models):
 	# onlinelda_test.py:14-35
 	W, D, K, alpha, eta = 102, 1010, 11, .27, 3.1
