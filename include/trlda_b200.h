@@ -34,7 +34,7 @@ extern "C" {
 #define TRLDA_OK            0
 #define TRLDA_ERR_ARG       1   /* reference would have thrown TRLDA::Exception -> RuntimeError */
 #define TRLDA_ERR_CUDA      2   /* CUDA / NCCL failure, or no device                              */
-#define TRLDA_ERR_UNSUPPORTED 3 /* e.g. inference_method == GIBBS (out of scope)  */
+#define TRLDA_ERR_UNSUPPORTED 3 /* e.g. inference_method == GIBBS in update_parameters / lower_bound     */
 
 /* model kinds: the three concrete subclasses of TRLDA::LDA */
 #define TRLDA_KIND_ONLINE     0   /* code/trlda/include/onlinelda.h:7     */
@@ -135,7 +135,11 @@ TRLDA_API int trlda_set_update_count(trlda_model* m, int64_t n);             /* 
 /* LDA::updateVariables (lda.cpp:119-156) -> LDA::updateVariablesVI (lda.cpp:160-220).
  * `latents` = initial gamma, K x B column-major, or NULL to draw gamma0 ~ Gamma(100, 1/100) on the device
  * (lda.cpp:135).  latents_rows/latents_cols are validated like lda.cpp:165 ("Initial gamma has wrong
- * dimensionality.").  gamma_out (K x B) and sstats_out (K x V) may each be NULL to skip the copy-out. */
+ * dimensionality.").  gamma_out (K x B) and sstats_out (K x V) may each be NULL to skip the copy-out.
+ * params->inference_method == TRLDA_INFERENCE_GIBBS runs LDA::updateVariablesGibbs (lda.cpp:224-293) instead:
+ * `latents` = initial theta (NULL: Dirichlet(1), lda.cpp:123-126), gamma_out receives theta ~ Dirichlet(counts),
+ * sstats_out the assignment counts averaged over params->num_samples sweeps after params->burn_in; the draws come
+ * from the library's counter-based generator (trlda_seed), not from rand(). */
 TRLDA_API int trlda_update_variables(trlda_model* m, const trlda_docs* docs,
                            const double* latents, int latents_rows, int64_t latents_cols,
                            const trlda_params* params, double* gamma_out, double* sstats_out);

@@ -91,8 +91,8 @@ def test_vi(models, oracle_built):
 	assert rel_err(sstats1, sstats0) < TOL_FP64
 	gamma2, _ = model1.update_variables(docs1, initial_gamma, 'VI', 50)
 	assert np.array_equal(gamma1, gamma2)
-	with pytest.raises(RuntimeError):                                         # Gibbs is out of scope
-		model1.update_variables(docs1, inference_method='gibbs')
+	theta, sstats3 = model1.update_variables(docs1, inference_method='gibbs')  # onlinelda_test.py:99-109; tests/test_gibbs_gpu.py
+	assert theta.shape == (K, D) and sstats3.shape == (K, W)
 	with pytest.raises(TypeError):
 		model1.update_variables(docs1, inference_method='xyz')
 	with pytest.raises(TypeError):

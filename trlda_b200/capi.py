@@ -292,8 +292,10 @@ class Model(object):
 		self._check(self._lib.trlda_set_precision(self.h, PRECISION[value]))
 
 	# ---- hot path -------------------------------------------------------------------------------------------------
-	def update_variables(self, docs, latents=None, max_iter=100, threshold=.001, want_sstats=True):
-		params = default_params(max_iter_inference=max_iter, threshold=threshold)
+	def update_variables(self, docs, latents=None, max_iter=100, threshold=.001, want_sstats=True, inference_method='VI',
+	                     num_samples=1, burn_in=2):
+		params = default_params(max_iter_inference=max_iter, threshold=threshold, num_samples=num_samples, burn_in=burn_in,
+			inference_method=1 if inference_method.upper() == 'GIBBS' else 0)
 		gamma = np.empty((self.K, docs.num_docs), order='F')
 		sstats = np.empty((self.K, self.V), order='F') if want_sstats else None
 		rows, cols = 0, 0

@@ -1104,6 +1104,183 @@ void launch_gamma_rng(double* out, int64_t n, uint64_t seed, uint64_t stream_id,
 		k_gamma_rng<<<(unsigned) ((n + 255) / 256), 256, 0, s>>>(out, n, seed, stream_id);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Collapsed Gibbs E-step (lda.cpp:224-293).  One warp per document (documents are independent given expElogbeta,
+// the sweep over a document's tokens is inherently sequential).  Per token occurrence the topic is drawn from
+// p(k) ~ expElogbeta[k, w] * counts[k] (counts = alpha + the document's other assignments): lane l owns the topics
+// k = l (mod 32), the 32 partial sums are scanned across the warp, the owning lane walks its topics.  Any fixed order
+// of the categories gives the same distribution; the reference's order (k ascending, utils.cpp:189-199) is not kept.
+// Random numbers: Philox4x32-10 keyed by the seed, counter = (document, draw) — results do not depend on the launch
+// shape.  Two deliberate departures from the reference, which is only smoke-tested there:
+//   * lda.cpp:254 initialises the assignments of document i from theta.col(j), j being the TOKEN index (reads past
+//     the matrix once a document has more pairs than the minibatch has documents); theta.col(i) is used here;
+//   * lda.cpp:284 adds into the shared sstats from all OpenMP threads without synchronisation; here atomicAdd.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double gibbs_uniform(uint64_t seed, uint32_t stream, uint64_t doc, uint32_t draw) {
+	uint32_t c[4] = {(uint32_t) doc, (uint32_t) (doc >> 32), stream, draw};
+	philox4x32(c, (uint32_t) seed, (uint32_t) (seed >> 32));
+	return ((double) c[0] * 4294967296.0 + (double) c[1]) * (1.0 / 18446744073709551616.0);   // [0, 1)
+}
+
+// Gamma(shape, 1), shape > 0: Marsaglia–Tsang for shape >= 1, boosted by U^(1/shape) below 1
+__device__ double gibbs_gamma(double shape, uint64_t seed, uint64_t doc, uint32_t element) {
+	const double a = shape < 1.0 ? shape + 1.0 : shape;
+	const double dd = a - 1.0 / 3.0, cc = 1.0 / sqrt(9.0 * dd);
+	double result = a;
+	for(uint32_t attempt = 0; attempt < 64; ++attempt) {
+		uint32_t c[4] = {(uint32_t) doc, (uint32_t) (doc >> 32) ^ (element << 8), 0x9e3779b9u + element, attempt};
+		philox4x32(c, (uint32_t) seed ^ 0x5bd1e995u, (uint32_t) (seed >> 32));
+		const double u1 = ((double) c[0] + 0.5) * (1.0 / 4294967296.0);
+		const double u2 = ((double) c[1] + 0.5) * (1.0 / 4294967296.0);
+		const double u3 = ((double) c[2] + 0.5) * (1.0 / 4294967296.0);
+		const double x = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+		const double t = 1.0 + cc * x;
+		if(t <= 0.0)
+			continue;
+		const double v = t * t * t;
+		if(log(u3) < 0.5 * x * x + dd - dd * v + dd * log(v)) {
+			result = dd * v;
+			if(shape < 1.0) {
+				const double u4 = ((double) c[3] + 0.5) * (1.0 / 4294967296.0);
+				result *= exp(log(u4) / shape);
+			}
+			break;
+		}
+	}
+	return result;
+}
+
+// draws k with probability proportional to beta_col[k] * factor[k]; all lanes return the same k
+template <typename TB>
+__device__ __forceinline__ int gibbs_draw(const TB* __restrict__ beta_col, const double* factor, int K, double u, int lane) {
+	double partial = 0.0;
+	for(int k = lane; k < K; k += 32)
+		partial += (double) beta_col[k] * factor[k];
+	double scan = partial;
+	#pragma unroll
+	for(int o = 1; o < 32; o <<= 1) {
+		const double other = __shfl_up_sync(0xffffffffu, scan, o);
+		if(lane >= o)
+			scan += other;
+	}
+	const double total = __shfl_sync(0xffffffffu, scan, 31);
+	const double r = u * total;
+	const unsigned above = __ballot_sync(0xffffffffu, scan > r && partial > 0.0);
+	// rounding can leave no lane above r: fall back to the last lane that has mass at all
+	const unsigned mass = __ballot_sync(0xffffffffu, partial > 0.0);
+	int owner = above ? __ffs(above) - 1 : (mass ? 31 - __clz(mass) : 0);
+	int k_found = owner < K ? owner : 0;
+	if(lane == owner) {
+		double left = r - (scan - partial);
+		int last = lane;
+		for(int k = lane; k < K; k += 32) {
+			const double w = (double) beta_col[k] * factor[k];
+			if(w > 0.0) {
+				last = k;
+				if(left < w)
+					break;
+				left -= w;
+			}
+		}
+		k_found = last;
+	}
+	return __shfl_sync(0xffffffffu, k_found, owner);
+}
+
+template <typename TB>
+__global__ void __launch_bounds__(128) k_gibbs(DeviceDocs docs, int K, const TB* __restrict__ beta, const double* __restrict__ alpha,
+                                                const double* __restrict__ theta0, const int64_t* __restrict__ occ_ptr,
+                                                uint16_t* __restrict__ topics, int num_samples, int burn_in, uint64_t seed,
+                                                double* __restrict__ theta_out, double* __restrict__ sstats) {
+	extern __shared__ __align__(16) unsigned char gibbs_smem[];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+	double* counts = reinterpret_cast<double*>(gibbs_smem) + (size_t) warp * K;
+	const double unit = 1.0 / (double) num_samples;                      // lda.cpp:232
+	for(int64_t d = (int64_t) blockIdx.x * warps + warp; d < docs.B; d += (int64_t) gridDim.x * warps) {
+		const int64_t begin = docs.doc_ptr[d], end = docs.doc_ptr[d + 1];
+		uint16_t* z = topics + occ_ptr[d];
+		uint32_t draw = 0;
+		// initial theta: the caller's (lda.cpp:142-147) or Dirichlet(1) (lda.cpp:123-126): normalised Exp(1) draws
+		double norm = 0.0;
+		for(int k = lane; k < K; k += 32) {
+			const double t = theta0 ? theta0[d * K + k] : -log(1.0 - gibbs_uniform(seed, 1u, (uint64_t) d, (uint32_t) k));
+			counts[k] = t;
+			norm += t;
+		}
+		norm = warp_sum(norm);
+		__syncwarp();
+		// initial assignments from p(k) ~ beta[k, w] theta[k] (blocked Gibbs, lda.cpp:247-263)
+		int64_t o = 0;
+		for(int64_t j = begin; j < end; ++j) {
+			const TB* col = beta + (int64_t) docs.word_ids[j] * K;
+			for(int c = 0; c < docs.counts[j]; ++c, ++o) {
+				const int k = gibbs_draw(col, counts, K, gibbs_uniform(seed, 2u, (uint64_t) d, draw++), lane);
+				if(lane == 0)
+					z[o] = (uint16_t) k;
+			}
+		}
+		__syncwarp();
+		// counts = alpha + occurrences of each topic (lda.cpp:244, 261)
+		for(int k = lane; k < K; k += 32)
+			counts[k] = alpha[k];
+		__syncwarp();
+		if(lane == 0)
+			for(int64_t i = 0; i < o; ++i)
+				counts[z[i]] += 1.0;
+		__syncwarp();
+		for(int s = 0; s < num_samples + burn_in; ++s) {                   // lda.cpp:265-288
+			o = 0;
+			for(int64_t j = begin; j < end; ++j) {
+				const int w = docs.word_ids[j];
+				const TB* col = beta + (int64_t) w * K;
+				for(int c = 0; c < docs.counts[j]; ++c, ++o) {
+					if(lane == 0)
+						counts[z[o]] -= 1.0;
+					__syncwarp();
+					const int k = gibbs_draw(col, counts, K, gibbs_uniform(seed, 3u, (uint64_t) d, draw++), lane);
+					if(lane == 0) {
+						z[o] = (uint16_t) k;
+						counts[k] += 1.0;
+						if(s >= burn_in)
+							atomicAdd(sstats + (int64_t) w * K + k, unit);     // lda.cpp:278-286
+					}
+					__syncwarp();
+				}
+			}
+		}
+		// theta ~ Dirichlet(counts) (lda.cpp:291)
+		double sum = 0.0;
+		for(int k = lane; k < K; k += 32) {
+			const double g = gibbs_gamma(counts[k], seed, (uint64_t) d, (uint32_t) k);
+			counts[k] = g;
+			sum += g;
+		}
+		sum = warp_sum(sum);
+		for(int k = lane; k < K; k += 32)
+			theta_out[d * K + k] = counts[k] / sum;
+		__syncwarp();
+	}
+}
+
+void launch_gibbs(const DeviceDocs& docs, int K, const void* beta, int beta_elem, const double* alpha, const double* theta0,
+                  const int64_t* occ_ptr, uint16_t* topics, int num_samples, int burn_in, uint64_t seed, double* theta_out,
+                  double* sstats, cudaStream_t s) {
+	if(docs.B == 0)
+		return;
+	const int warps = 4;
+	const size_t smem = (size_t) warps * K * sizeof(double);
+	const unsigned grid = (unsigned) std::min<int64_t>((docs.B + warps - 1) / warps, 148 * 8);
+	if(beta_elem == 4) {
+		cudaFuncSetAttribute(k_gibbs<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+		k_gibbs<float><<<grid, warps * 32, smem, s>>>(docs, K, static_cast<const float*>(beta), alpha, theta0, occ_ptr, topics,
+		                                              num_samples, burn_in, seed, theta_out, sstats);
+	} else {
+		cudaFuncSetAttribute(k_gibbs<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+		k_gibbs<double><<<grid, warps * 32, smem, s>>>(docs, K, static_cast<const double*>(beta), alpha, theta0, occ_ptr, topics,
+		                                               num_samples, burn_in, seed, theta_out, sstats);
+	}
+}
+
 __global__ void k_fill(double* __restrict__ out, int64_t n, double v) {
 	const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
 	if(i < n)

@@ -104,6 +104,12 @@ bool stream_estep_applicable(int K, int n_max, int elem_size, int smem_optin);
 void launch_estep_stream(const EStepArgs& args, const DeviceDocs& docs, const int32_t* order, int64_t offset,
                          int64_t count, int n_max, int elem_size, bool cold, cudaStream_t s);
 
+// collapsed Gibbs E-step (lda.cpp:224-293): theta_out K x B, sstats K x V (zeroed by the caller), topics = scratch of one
+// uint16 per token occurrence, occ_ptr[d] = occurrences before document d
+void launch_gibbs(const DeviceDocs& docs, int K, const void* beta, int beta_elem, const double* alpha, const double* theta0,
+                  const int64_t* occ_ptr, uint16_t* topics, int num_samples, int burn_in, uint64_t seed, double* theta_out,
+                  double* sstats, cudaStream_t s);
+
 constexpr int TRLDA_MAX_RANKS = 8;    // one NVSwitch node
 
 // segmented scatter.  If `fused`, lambda/beta are rebuilt in the same pass (single-GPU path); else the dense

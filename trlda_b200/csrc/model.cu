@@ -235,6 +235,7 @@ struct trlda_model {
 
 	// per-minibatch E-step buffers
 	DevBuf gamma, etheta, etheta32, weight, doc_stat, iterations;
+	DevBuf gibbs_occ, gibbs_topics;            // Gibbs E-step scratch: occurrences before each document, one topic per occurrence
 	bool gamma_valid = false;
 
 	// parity seams
@@ -1509,7 +1510,7 @@ void trlda_destroy(trlda_model* m) {
 	DevBuf* bufs[] = {&m->ada_gradient, &m->lam[0], &m->lam[1], &m->beta, &m->sstats, &m->sstats32, &m->rows, &m->rows_prev, &m->rows_stat,
 	                  &m->psi_rows, &m->d_alpha, &m->partials, &m->vpartials, &m->scalars, &m->b_doc_ptr, &m->b_word_ids,
 	                  &m->b_counts, &m->b_word_ptr, &m->b_tok_doc, &m->b_tok_src, &m->b_order, &m->wordcount, &m->gamma, &m->etheta,
-	                  &m->etheta32, &m->weight, &m->doc_stat, &m->iterations};
+	                  &m->etheta32, &m->weight, &m->doc_stat, &m->iterations, &m->gibbs_occ, &m->gibbs_topics};
 	for(DevBuf* b : bufs)
 		b->release();
 	for(auto& slot : m->slots) {
@@ -1684,10 +1685,63 @@ int trlda_select_docs(trlda_model* m, int slot) {
 	return TRLDA_OK;
 }
 
+// LDA::updateVariablesGibbs (lda.cpp:224-293) for the documents of `docs`: theta (K x B) and sstats (K x V, each token
+// occurrence contributes 1/num_samples per collected sweep).  Only reachable through trlda_update_variables, like the
+// reference's tests reach it; the parameter updates stay variational.
+static int gibbs_variables(trlda_model* m, const trlda_docs* docs, const double* latents, int latents_rows,
+                           int64_t latents_cols, const trlda_params* params, double* theta_out, double* sstats_out) {
+	if(latents && (latents_rows != m->K || latents_cols != docs->num_docs))
+		return fail(m, TRLDA_ERR_ARG, "Initial theta has wrong dimensionality.");   // lda.cpp:228
+	if(params->num_samples < 1 || params->burn_in < 0)
+		return fail(m, TRLDA_ERR_ARG, "num_samples should be positive and burn_in non-negative.");
+	if(m->nranks > 1)
+		return fail(m, TRLDA_ERR_UNSUPPORTED, "The Gibbs E-step is not sharded over GPUs.");
+	TRY(upload_docs(m, docs));
+	TRY(prepare_beta(m));
+	const int64_t B = m->docs.B;
+	const size_t kb = sizeof(double) * (size_t) m->K * (size_t) B;
+	std::vector<int64_t> occ((size_t) B + 1, 0);
+	for(int64_t d = 0; d < B; ++d) {
+		int64_t total = 0;
+		for(int64_t j = docs->doc_ptr[d]; j < docs->doc_ptr[d + 1]; ++j)
+			total += docs->counts[j];
+		occ[(size_t) d + 1] = occ[(size_t) d] + total;
+	}
+	CUDA_TRY(m, m->gibbs_occ.ensure(sizeof(int64_t) * ((size_t) B + 1)));
+	CUDA_TRY(m, m->gibbs_topics.ensure(sizeof(uint16_t) * (size_t) std::max<int64_t>(occ[(size_t) B], 1)));
+	CUDA_TRY(m, m->sstats.ensure(kv_bytes(m)));
+	CUDA_TRY(m, cudaMemcpyAsync(m->gibbs_occ.p, occ.data(), sizeof(int64_t) * ((size_t) B + 1), cudaMemcpyHostToDevice, m->stream));
+	CUDA_TRY(m, cudaMemsetAsync(m->sstats.p, 0, kv_bytes(m), m->stream));
+	if(latents && B) {
+		CUDA_TRY(m, cudaMemcpyAsync(m->etheta.p, latents, kb, cudaMemcpyHostToDevice, m->stream));
+		m->stats.h2d_bytes += kb;
+	}
+	{
+		Launch l(m, KK_ESTEP);
+		launch_gibbs(m->docs, m->K, m->beta.p, m->beta_elem, m->d_alpha.as<double>(), latents ? m->etheta.as<double>() : nullptr,
+		             m->gibbs_occ.as<int64_t>(), m->gibbs_topics.as<uint16_t>(), params->num_samples, params->burn_in,
+		             current_seed() ^ (next_stream_id() * 0x9E3779B97F4A7C15ull), m->gamma.as<double>(), m->sstats.as<double>(),
+		             m->stream);
+	}
+	TRY(check_launch(m, "gibbs"));
+	m->gamma_valid = false;                      // the buffer holds theta, not a variational gamma
+	if(theta_out && B) {
+		CUDA_TRY(m, cudaMemcpyAsync(theta_out, m->gamma.p, kb, cudaMemcpyDeviceToHost, m->stream));
+		m->stats.d2h_bytes += kb;
+	}
+	if(sstats_out) {
+		CUDA_TRY(m, cudaMemcpyAsync(sstats_out, m->sstats.p, kv_bytes(m), cudaMemcpyDeviceToHost, m->stream));
+		m->stats.d2h_bytes += kv_bytes(m);
+	}
+	CUDA_TRY(m, cudaStreamSynchronize(m->stream));   // occ (host vector) must outlive its copy
+	consume_injections(m);
+	return TRLDA_OK;
+}
+
 int trlda_update_variables(trlda_model* m, const trlda_docs* docs, const double* latents, int latents_rows,
                            int64_t latents_cols, const trlda_params* params, double* gamma_out, double* sstats_out) {
-	if(params->inference_method != TRLDA_INFERENCE_VI)
-		return fail(m, TRLDA_ERR_UNSUPPORTED, "Only variational inference ('VI') is implemented on the device.");
+	if(params->inference_method == TRLDA_INFERENCE_GIBBS)
+		return gibbs_variables(m, docs, latents, latents_rows, latents_cols, params, gamma_out, sstats_out);
 	if(latents && (latents_rows != m->K || latents_cols != docs->num_docs))
 		return fail(m, TRLDA_ERR_ARG, "Initial gamma has wrong dimensionality.");   // lda.cpp:166
 	TRY(upload_docs(m, docs));
