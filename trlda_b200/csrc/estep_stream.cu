@@ -38,9 +38,9 @@ __device__ __forceinline__ void svec_get(const float4& v, float (&o)[4]) { o[0] 
 __device__ __forceinline__ void svec_get(const double2& v, double (&o)[2]) { o[0] = v.x; o[1] = v.y; }
 
 
-// how many per-warp partial vectors meet in shared memory at once: above 32 KB the warps fold pairwise first
+// how many per-warp partial vectors meet in shared memory at once: above 64 KB the warps fold pairwise first
 __host__ __device__ constexpr int stream_reduce_width(int NW, int kp, int elem) {
-	return (NW * kp * elem > 32768 && NW % 2 == 0) ? NW / 2 : NW;
+	return (NW * kp * elem > 65536 && NW % 2 == 0) ? NW / 2 : NW;
 }
 
 struct StreamSmem {
@@ -432,9 +432,13 @@ k_estep_stream(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, 
 					for(int src = 0; src < C; ++src)
 						total[u] += (double) xall[(size_t) (buf * C + src) * KP + r];   // rank order: identical bits in every CTA
 				} else {
+					// the partials are T: they are added in T (mixed mode: one float32 rounding per partial, like the
+					// accumulators themselves) and converted once — F2F.F64.F32 per partial was a cost of its own
+					T part = red[r];
 					#pragma unroll
-					for(int q = 0; q < RW; ++q)
-						total[u] += (double) red[(size_t) q * KP + r];
+					for(int q = 1; q < RW; ++q)
+						part += red[(size_t) q * KP + r];
+					total[u] = (double) part;
 				}
 				eo[u] = (double) eth[r];
 			}
