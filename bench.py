@@ -180,9 +180,9 @@ def cpu_sample(w, docs, lam0, sizes, workload_name):
 	T = params['max_iter_tr']
 	b1, b2 = sizes
 	runs = [(b1, 1), (b2, 1), (b1, 2)]
-	times = []
 	start_all = time.perf_counter()
-	for n, iters in runs:
+
+	def timed(n, iters):
 		csr = pyoracle.CSR(ptr[:n + 1], ids[:ptr[n]], cts[:ptr[n]])
 		g0 = gamma_matrix(w['K'], n, 3000 + CFG_INDEX[workload_name])
 		model.lambdas = lam0
@@ -190,7 +190,15 @@ def cpu_sample(w, docs, lam0, sizes, workload_name):
 		params['max_iter_tr'] = iters
 		t0 = time.perf_counter()
 		model.update_parameters(csr, gamma0=g0, **params)
-		times.append(time.perf_counter() - t0)
+		return time.perf_counter() - t0
+
+	# the first call of a process pays for the page faults of its K x V temporaries: one untimed call, and the small run is
+	# timed before and after the others (the smaller of the two counts)
+	if not _CPU_MODEL.get('warm'):
+		timed(b1, 1)
+		_CPU_MODEL['warm'] = True
+	times = [timed(n, iters) for n, iters in runs]
+	times[0] = min(times[0], timed(b1, 1))
 	spent = time.perf_counter() - start_all
 	b = max((times[1] - times[0]) / (b2 - b1), 1e-9)
 	per_iter = max(times[2] - times[0], 1e-9)              # a + b * b1
@@ -211,10 +219,10 @@ def reference_arm(args, w):
 	rank = int(os.environ.get('RANK', '0'))
 	if rank != 0:
 		return
-	docs, lam0 = make_inputs(w, 512, 0, args.workload)
+	docs, lam0 = make_inputs(w, 2048, 0, args.workload)
 	cores = os.cpu_count() or 1
 	os.environ.setdefault('OMP_NUM_THREADS', str(cores))
-	sizes = [64, 512]
+	sizes = [64, 2048]     # the per-document slope needs a sample whose cost stands out of the ~3.5 s of fixed K*V work
 	# CPU code needs no warm-up beyond the first call; keep the whole run within a few minutes
 	total_steps = args.steps + args.warmup
 	values, fulls = [], []
@@ -390,7 +398,7 @@ def main():
 		'roofline': roofline}
 
 	if rank == 0 and world == 1 and not args.no_cpu_baseline:
-		sizes = [64, min(512, B)]
+		sizes = [64, min(2048, B)]     # the per-document slope needs a sample whose cost stands out of the ~3.5 s of fixed K*V work
 		cpu_value, full, spent, kind, text = cpu_sample(w, docs_np, lam0, sizes, args.workload)
 		line['cpu_baseline'] = {
 			'value': cpu_value, 'unit': 'docs/s', 'cores': int(os.environ.get('OMP_NUM_THREADS', os.cpu_count() or 1)),
