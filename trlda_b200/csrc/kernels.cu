@@ -654,6 +654,19 @@ __global__ void __launch_bounds__(NT, (NT == 128 && NCH <= 2 ? 5 : 1)) k_scatter
 		for(int q = 0; q < 4; ++q)
 			ek[i][q] = (a.fused && a.write_beta && c < chunks) ? (float) exp(-a.psi_rows[4 * c + q]) : 0.0f;
 	}
+	__shared__ int s_doc[2][NT];
+	__shared__ float s_w[2][NT];
+	auto stage_tokens = [&](int b, int begin, int end) {
+		const int t = begin + (int) threadIdx.x;
+		if(t < end) {
+			s_doc[b][threadIdx.x] = docs.tok_doc[t];
+			s_w[b][threadIdx.x] = (float) a.weight[docs.tok_src[t]];
+		}
+	};
+	int buf = 0;
+	if((int) blockIdx.x < a.V)
+		stage_tokens(0, docs.word_ptr[blockIdx.x], docs.word_ptr[blockIdx.x + 1]);
+	__syncthreads();
 	for(int w = blockIdx.x; w < a.V; w += gridDim.x) {
 		const int64_t base = (int64_t) w * K;
 		float4 bcol[NCH];
@@ -676,51 +689,50 @@ __global__ void __launch_bounds__(NT, (NT == 128 && NCH <= 2 ? 5 : 1)) k_scatter
 			acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.0;
 
 		const int t0 = docs.word_ptr[w], t1 = docs.word_ptr[w + 1];
-		int dd[G];
-		double ww[G];
-		auto fetch = [&](int t) {
-			#pragma unroll
-			for(int u = 0; u < G; ++u) {
-				const bool ok = t + u < t1;
-				dd[u] = ok ? docs.tok_doc[t + u] : 0;
-				ww[u] = ok ? a.weight[docs.tok_src[t + u]] : 0.0;
+		// the (document, weight) pairs of the word's tokens were staged into shared memory while the previous word was
+		// processed (one cooperative round of the dependent loads tok_src -> weight instead of one per token group);
+		// now the next word's are requested
+		const int wn = w + gridDim.x;
+		if(wn < a.V)
+			stage_tokens(buf ^ 1, docs.word_ptr[wn], docs.word_ptr[wn + 1]);
+		for(int ts = t0; ts < t1; ts += NT) {
+			if(ts > t0) {                                              // words with more than NT tokens: restage in place
+				__syncthreads();
+				stage_tokens(buf, ts, t1);
+				__syncthreads();
 			}
-		};
-		if(t0 < t1)
-			fetch(t0);
-		for(int t = t0; t < t1; t += G) {
-			float4 v[G][NCH];
-			#pragma unroll
-			for(int u = 0; u < G; ++u) {
-				const float4* col = reinterpret_cast<const float4*>(etheta + (int64_t) dd[u] * K);
-				#pragma unroll
-				for(int i = 0; i < NCH; ++i) {
-					const int c = threadIdx.x + i * NT;
-					v[u][i] = c < chunks ? col[c] : make_float4(0.f, 0.f, 0.f, 0.f);
-				}
-			}
-			double wc[G];
-			#pragma unroll
-			for(int u = 0; u < G; ++u)
-				wc[u] = ww[u];
-			if(t + G < t1)
-				fetch(t + G);
-			// float32 products summed over the <= G tokens of the group, float64 across groups
-			#pragma unroll
-			for(int i = 0; i < NCH; ++i) {
-				float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
+			const int n = min(NT, t1 - ts);
+			for(int g = 0; g < n; g += G) {
+				float4 v[G][NCH];
+				float wf[G];
 				#pragma unroll
 				for(int u = 0; u < G; ++u) {
-					const float wf = (float) wc[u];
-					g0 = fmaf(wf, v[u][i].x, g0);
-					g1 = fmaf(wf, v[u][i].y, g1);
-					g2 = fmaf(wf, v[u][i].z, g2);
-					g3 = fmaf(wf, v[u][i].w, g3);
+					const bool live = g + u < n;                             // no dummy gathers for the tail of a group
+					const int dd = live ? s_doc[buf][g + u] : 0;
+					wf[u] = live ? s_w[buf][g + u] : 0.f;
+					const float4* col = reinterpret_cast<const float4*>(etheta + (int64_t) dd * K);
+					#pragma unroll
+					for(int i = 0; i < NCH; ++i) {
+						const int c = threadIdx.x + i * NT;
+						v[u][i] = (live && c < chunks) ? col[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+					}
 				}
-				acc[i][0] += (double) g0;
-				acc[i][1] += (double) g1;
-				acc[i][2] += (double) g2;
-				acc[i][3] += (double) g3;
+				// float32 products summed over the <= G tokens of the group, float64 across groups
+				#pragma unroll
+				for(int i = 0; i < NCH; ++i) {
+					float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
+					#pragma unroll
+					for(int u = 0; u < G; ++u) {
+						g0 = fmaf(wf[u], v[u][i].x, g0);
+						g1 = fmaf(wf[u], v[u][i].y, g1);
+						g2 = fmaf(wf[u], v[u][i].z, g2);
+						g3 = fmaf(wf[u], v[u][i].w, g3);
+					}
+					acc[i][0] += (double) g0;
+					acc[i][1] += (double) g1;
+					acc[i][2] += (double) g2;
+					acc[i][3] += (double) g3;
+				}
 			}
 		}
 
@@ -781,6 +793,8 @@ __global__ void __launch_bounds__(NT, (NT == 128 && NCH <= 2 ? 5 : 1)) k_scatter
 			if(threadIdx.x == 0)
 				a.psi_partials[w] = total;
 		}
+		__syncthreads();       // the next word's tokens are staged, this word's buffer is free
+		buf ^= 1;
 	}
 }
 
