@@ -1,11 +1,12 @@
 """Turns the ncu outputs brought back in gpurun_out/ into the tracked summaries under profiles/.
 
-    python scripts/summarize_profiles.py <launches.csv> <full.ncu-rep> <tag>
+    python scripts/summarize_profiles.py <launches.csv> <full.ncu-rep> <tag> [<estep_traffic.csv>]
 """
 import collections, csv, os, subprocess, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 launches, rep, tag = sys.argv[1:4]
+traffic = sys.argv[4] if len(sys.argv) > 4 else None
 
 # ---- launch list: per-kernel totals and shares -----------------------------------------------------------------------
 with open(launches) as f:
@@ -59,6 +60,33 @@ for i, r in enumerate(body):
 		float(g('dram__bytes_read.sum')), float(g('dram__bytes_write.sum')),
 		float(g('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed')), float(g('lts__t_sector_hit_rate.pct')),
 		float(g('smsp__issue_active.avg.pct_of_peak_sustained_active')), g('launch__registers_per_thread')))
+# ---- E-step launch by launch (metrics pass over k_estep_stream only) ----------------------------------------------------
+if traffic:
+	import shutil
+	shutil.copyfile(traffic, os.path.join(ROOT, 'profiles', '%s_estep_traffic.csv' % tag))
+	with open(traffic) as f:
+		trows = list(csv.DictReader([l for l in f if not l.startswith('==')]))
+	per = collections.defaultdict(dict)
+	for r in trows:
+		per[int(r['ID'])][r['Metric Name']] = (float(r['Metric Value'].replace(',', '')), r['Metric Unit'])
+	scale = {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1, 'ms': 1e-3, 'us': 1e-6, 'ns': 1e-9, 's': 1, '%': 1}
+	summary += ['', '## k_estep_stream, launch by launch (%s_estep_traffic.csv)' % tag, '',
+		'`ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sector_hit_rate.pct,'
+		'l1tex__m_xbar2l1tex_read_bytes.sum -k regex:k_estep_stream -c 30 python bench.py --steps 2 --warmup 1`:',
+		'three update_parameters steps of ten trust-region iterations each.  The first E-steps of a step run the full 20 inner',
+		'iterations (21 sweeps of the 4.9 GB of tiles = 103 GB from L2 to the SMs); the later ones start from a converged',
+		'gamma and stop after one inner iteration (2 sweeps).', '',
+		'| launch | ms | HBM read GB | HBM write GB | L2 hit % | L2 -> SM GB | L2 -> SM TB/s |', '|---:|---:|---:|---:|---:|---:|---:|']
+	tot = [0., 0., 0., 0.]
+	for i in sorted(per):
+		m = per[i]
+		v = lambda k: m[k][0] * scale.get(m[k][1], 1)
+		t, rd, wr, l2 = v('gpu__time_duration.sum'), v('dram__bytes_read.sum'), v('dram__bytes_write.sum'), v('l1tex__m_xbar2l1tex_read_bytes.sum')
+		tot = [tot[0] + t, tot[1] + rd, tot[2] + wr, tot[3] + l2]
+		summary.append('| %d | %.2f | %.2f | %.2f | %.0f | %.1f | %.1f |' % (i, t * 1e3, rd / 1e9, wr / 1e9, m['lts__t_sector_hit_rate.pct'][0], l2 / 1e9, l2 / t / 1e12))
+	n = len(per)
+	summary.append('| mean | %.2f | %.2f | %.2f | | %.1f | %.1f |' % (tot[0] / n * 1e3, tot[1] / n / 1e9, tot[2] / n / 1e9, tot[3] / n / 1e9, tot[3] / tot[0] / 1e12))
+
 with open(os.path.join(ROOT, 'profiles', '%s_summary.md' % tag), 'w') as f:
 	f.write('\n'.join(summary) + '\n')
 print('\n'.join(summary))
