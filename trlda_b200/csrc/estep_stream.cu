@@ -1,9 +1,10 @@
 // estep_stream.cu — the per-document E-step (lda.cpp:174-204 of the reference), streaming design (the default path).
 //
-// The K x n_d tile of expElogbeta columns of a document is NOT kept on chip; it is streamed once per inner iteration:
-// every warp pulls its own columns (K contiguous values each) through a private shared-memory ring with 16-byte
-// `cp.async` (no block-wide barrier on the data path), and — because a warp sees a complete column — the two passes
-// of the reference's inner iteration fuse into ONE sweep:
+// The K x n_d tile of expElogbeta columns of a document is NOT kept on chip (150 columns x 4 KB at cfg-3: no SM holds
+// it); it is streamed once per inner iteration.  Every warp pulls its own columns (K contiguous values each) through a
+// private shared-memory ring — one `cp.async.bulk` per column, issued by one lane, completing on the slot's mbarrier
+// (16-byte `cp.async` for columns shorter than 2 KB); there is no block-wide barrier on the data path — and, because a
+// warp sees a complete column, the two passes of the reference's inner iteration fuse into ONE sweep:
 //
 //     phi_j = etheta . col_j  (+1e-100)      lda.cpp:183,199      warp-shuffle reduction over the K rows
 //     W_j   = c_j / phi_j                    lda.cpp:192
@@ -12,16 +13,13 @@
 // After a sweep the per-warp partial sums meet in shared memory (fixed order: deterministic), gamma and
 // exp(psi(gamma)) are updated (lda.cpp:194-197) and the convergence test of lda.cpp:202 is evaluated.  I inner
 // iterations cost I+1 sweeps (the last one produces the token weights and the document's share of the row sums of
-// the sufficient statistics); the first sweep comes from HBM, the re-sweeps should come from L2.
+// the sufficient statistics); the first sweep comes from HBM, the re-sweeps from L2 (148 documents x 600 KB in flight).
 //
-// That last point decides the shape.  With one document per SM the tiles in flight are 148 x ~600 KB at cfg-3 —
-// more than the L2 keeps (ncu: 77 % of the re-sweep bytes came from DRAM).  So a document is given to a CLUSTER of
-// C CTAs (C = 2 by default) that split its COLUMNS: each SM streams 1/C of the tile, the tiles in flight shrink to
-// 148 x 600/C KB and stay L2-resident, and the only cross-CTA traffic per sweep is one K-vector of partial sums,
-// sent to every peer with one DSMEM bulk copy (`cp.async.bulk.shared::cluster.shared::cta`) that completes on the
-// receiver's mbarrier.  Every CTA adds the C partial vectors in rank order — identical bits everywhere — and
-// updates gamma / exp(psi(gamma)) redundantly, so the convergence decision is cluster-uniform without further
-// exchange and the result does not depend on timing.
+// Launch shape: one CTA of 16 warps per document (fp32 tile; 8 warps for the fp64 tile and for short columns), handed
+// out by the hardware scheduler.  Kept behind environment switches because they were measured, and lost:
+// a CLUSTER of C CTAs per document that split its COLUMNS and exchange one K-vector of partial sums per sweep by DSMEM
+// bulk copies (every CTA then adds the C partial vectors in rank order — identical bits everywhere — and updates gamma
+// redundantly); a persistent grid with fewer documents in flight; deeper rings with fewer warps.
 #include "kernels.cuh"
 #include "special.cuh"
 
