@@ -223,6 +223,123 @@ static double* exp_elog_beta(const oracle_model* m) {
 	return out;
 }
 
+/* ---- LDA::updateVariablesGibbs (lda.cpp:224-293), restated WITHOUT its two defects --------------------------------
+ *  (a) lda.cpp:254 reads theta.col(j) with j the token index; the document's own column theta.col(i) is meant;
+ *  (b) lda.cpp:284 adds into sstats from all OpenMP threads unsynchronised; this restatement is serial.
+ * Uniforms are rand() / (RAND_MAX + 1) (utils.cpp:203-206) and a topic is picked by walking the histogram in topic
+ * order (sampleHistogram, utils.cpp:189-199).  The final theta ~ Dirichlet(counts) (lda.cpp:291) uses
+ * std::gamma_distribution on an mt19937 in the reference, which plain C cannot replay: Marsaglia-Tsang on rand() here
+ * — the law is the same, the stream is not.  Parity with the CUDA kernel is therefore distributional (the kernel has
+ * its own counter-based generator anyway); tests/test_oracle.py and tests/test_gibbs_gpu.py hold the properties. */
+static double gibbs_uniform01(void) {
+	return (double) rand() / ((double) RAND_MAX + 1.0);
+}
+
+static int gibbs_histogram(const double* weight, int K) {
+	double total = 0.0;
+	for(int k = 0; k < K; ++k)
+		total += weight[k];
+	double r = gibbs_uniform01() * total;
+	int last = 0;
+	for(int k = 0; k < K; ++k) {
+		if(weight[k] > 0.0)
+			last = k;
+		if(r < weight[k])
+			return k;
+		r -= weight[k];
+	}
+	return last;                                                  /* utils.cpp:198 throws here */
+}
+
+static double gibbs_gamma_draw(double shape) {
+	const double a = shape < 1.0 ? shape + 1.0 : shape;
+	const double d = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+	for(;;) {
+		const double u1 = (gibbs_uniform01() * RAND_MAX + 0.5) / ((double) RAND_MAX + 1.0);
+		const double u2 = gibbs_uniform01();
+		const double x = sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2);
+		const double t = 1.0 + c * x;
+		if(t <= 0.0)
+			continue;
+		const double v = t * t * t;
+		const double u3 = (gibbs_uniform01() * RAND_MAX + 0.5) / ((double) RAND_MAX + 1.0);
+		if(log(u3) < 0.5 * x * x + d - d * v + d * log(v)) {
+			double g = d * v;
+			if(shape < 1.0) {
+				const double u4 = (gibbs_uniform01() * RAND_MAX + 0.5) / ((double) RAND_MAX + 1.0);
+				g *= exp(log(u4) / shape);
+			}
+			return g;
+		}
+	}
+}
+
+int oracle_update_variables_gibbs(const oracle_model* m, const trlda_docs* docs, const double* theta0,
+                                  int num_samples, int burn_in, double* theta_out, double* sstats_out)
+{
+	const int K = m->K, V = m->V;
+	const int64_t B = docs->num_docs;
+	const double unit = 1.0 / num_samples;                        /* :232 */
+	double* beta = exp_elog_beta(m);                              /* :235-236 */
+	double* counts = (double*) malloc(sizeof(double) * K);
+	double* dist = (double*) malloc(sizeof(double) * K);
+	if(sstats_out)
+		memset(sstats_out, 0, sizeof(double) * (size_t) K * V);   /* :230 */
+
+	for(int64_t d = 0; d < B; ++d) {
+		const int64_t begin = docs->doc_ptr[d], end = docs->doc_ptr[d + 1];
+		int64_t occurrences = 0;
+		for(int64_t j = begin; j < end; ++j)
+			occurrences += docs->counts[j];
+		int* topics = (int*) malloc(sizeof(int) * (size_t) (occurrences ? occurrences : 1));
+		const double* theta = theta0 + (size_t) d * K;            /* (a): column of the DOCUMENT */
+		for(int k = 0; k < K; ++k)
+			counts[k] = m->alpha[k];                              /* :244 */
+
+		int64_t o = 0;
+		for(int64_t j = begin; j < end; ++j) {                    /* :247-263 */
+			const double* col = beta + (size_t) docs->word_ids[j] * K;
+			for(int k = 0; k < K; ++k)
+				dist[k] = col[k] * theta[k];
+			for(int c = 0; c < docs->counts[j]; ++c, ++o) {
+				topics[o] = gibbs_histogram(dist, K);
+				counts[topics[o]] += 1.0;
+			}
+		}
+		for(int s = 0; s < num_samples + burn_in; ++s) {          /* :265-288 */
+			o = 0;
+			for(int64_t j = begin; j < end; ++j) {
+				const int w = docs->word_ids[j];
+				const double* col = beta + (size_t) w * K;
+				for(int c = 0; c < docs->counts[j]; ++c, ++o) {
+					counts[topics[o]] -= 1.0;
+					for(int k = 0; k < K; ++k)
+						dist[k] = col[k] * counts[k];
+					topics[o] = gibbs_histogram(dist, K);
+					counts[topics[o]] += 1.0;
+					if(s >= burn_in && sstats_out)
+						sstats_out[(size_t) w * K + topics[o]] += unit;
+				}
+			}
+		}
+		if(theta_out) {                                           /* :291 */
+			double sum = 0.0;
+			double* out = theta_out + (size_t) d * K;
+			for(int k = 0; k < K; ++k) {
+				out[k] = gibbs_gamma_draw(counts[k]);
+				sum += out[k];
+			}
+			for(int k = 0; k < K; ++k)
+				out[k] /= sum;
+		}
+		free(topics);
+	}
+	free(dist);
+	free(counts);
+	free(beta);
+	return 0;
+}
+
 int oracle_update_variables(const oracle_model* m, const trlda_docs* docs, const double* gamma0,
                             int max_iter, double threshold, double* gamma_out, double* sstats_out,
                             int* iterations_out)

@@ -50,6 +50,11 @@ int oracle_update_variables(const oracle_model* m, const trlda_docs* docs, const
  * internal fresh draw of gamma (NULL: draw from rand() like utils.cpp:224-231); lambda0 replaces the random
  * re-initialisation of cumulativelda.cpp:60 (NULL: draw).  gamma_out (K x B, may be NULL) receives the gamma of
  * the last E-step. */
+/* LDA::updateVariablesGibbs (lda.cpp:224-293) with its index bug (:254) and data race (:284) removed; theta0 is K x B,
+ * theta_out K x B, sstats_out K x V (either may be NULL); draws from rand() */
+int oracle_update_variables_gibbs(const oracle_model* m, const trlda_docs* docs, const double* theta0,
+                                  int num_samples, int burn_in, double* theta_out, double* sstats_out);
+
 double oracle_update_parameters(oracle_model* m, const trlda_docs* docs, const trlda_params* p,
                                 const double* gamma0, const double* lambda0, double* gamma_out);
 

@@ -215,6 +215,9 @@ def port_lib():
 	lib.oracle_update_variables.argtypes = [
 		C.POINTER(OracleModelStruct), C.POINTER(Docs), C.POINTER(C.c_double), C.c_int, C.c_double,
 		C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]
+	lib.oracle_update_variables_gibbs.argtypes = [
+		C.POINTER(OracleModelStruct), C.POINTER(Docs), C.POINTER(C.c_double), C.c_int, C.c_int,
+		C.POINTER(C.c_double), C.POINTER(C.c_double)]
 	lib.oracle_update_parameters.restype = C.c_double
 	lib.oracle_update_parameters.argtypes = [
 		C.POINTER(OracleModelStruct), C.POINTER(Docs), C.POINTER(Params), C.POINTER(C.c_double),
@@ -435,6 +438,21 @@ class PortModel(object):
 		if want_iterations:
 			return gamma, sstats, iterations
 		return gamma, sstats
+
+	def update_variables_gibbs(self, docs, theta0=None, num_samples=1, burn_in=2, seed=None):
+		"""lda.cpp:224-293 without its index bug and race (see lda_oracle.c); theta0 defaults to Dirichlet(1) columns
+		(lda.cpp:123-126) drawn with numpy"""
+		if theta0 is None:
+			theta0 = np.random.dirichlet(np.ones(self.K), size=docs.num_docs).T
+		theta0 = _fortran(theta0)
+		if theta0.shape != (self.K, docs.num_docs):
+			raise RuntimeError('Initial theta has wrong dimensionality.')
+		if seed is not None:
+			C.CDLL(None).srand(seed)
+		theta = np.empty((self.K, docs.num_docs), order='F')
+		sstats = np.empty((self.K, self.V), order='F')
+		self.lib.oracle_update_variables_gibbs(self.m, C.byref(docs.c), _dptr(theta0), num_samples, burn_in, _dptr(theta), _dptr(sstats))
+		return theta, sstats
 
 	def update_parameters(self, docs, gamma0=None, lambda0=None, seed=None, want_gamma=False, **kwargs):
 		params = Params(**kwargs)

@@ -186,3 +186,42 @@ def test_fast_constructed_reference_is_the_same_model(oracle_built):
 	assert np.allclose(out[0][1], out[1][1], rtol=1e-12, atol=0) and np.allclose(out[0][2], out[1][2], rtol=1e-12, atol=0)
 	with pytest.raises(RuntimeError):
 		oracle_built.RefModel('online', V, K, 300, .1, .2, fast_init=True).update_parameters(docs, gamma0=g0, adaptive=1)
+
+
+def test_gibbs_restatement_properties(oracle_built):
+	"""the corrected restatement of lda.cpp:224-293 (no reference output can pin it: the original indexes theta by token,
+	lda.cpp:254, and races on sstats, :284): counts conserved, forced assignments exact, seeded runs reproducible, and
+	many sweeps agree with the variational sufficient statistics — the same properties tests/test_gibbs_gpu.py asks of
+	the CUDA kernel"""
+	from common import random_docs
+	rng = np.random.default_rng(31)
+	K, V, B = 4, 40, 25
+	lam = np.full((K, V), 1e-16)
+	for k in range(K):
+		lam[k, 10 * k:10 * k + 10] = 50.
+	model = oracle_built.PortModel('online', V, K, 1000, .1, .2)
+	model.lambdas = np.asfortranarray(lam)
+	docs = oracle_built.CSR.from_lists(random_docs(rng, B, V, 25) + [[]])
+	totals = np.zeros(V)
+	np.add.at(totals, docs.word_ids, docs.counts)
+	theta0 = rng.dirichlet(np.ones(K), size=B + 1).T
+	theta, sstats = model.update_variables_gibbs(docs, theta0, num_samples=3, burn_in=1, seed=4)
+	expected = np.zeros((K, V))
+	for k in range(K):
+		expected[k, 10 * k:10 * k + 10] = totals[10 * k:10 * k + 10]
+	assert np.allclose(sstats, expected, rtol=0, atol=1e-9)
+	assert np.all(theta > 0) and np.allclose(theta.sum(0), 1., rtol=0, atol=1e-12)
+	again = model.update_variables_gibbs(docs, theta0, num_samples=3, burn_in=1, seed=4)
+	assert np.array_equal(theta, again[0]) and np.array_equal(sstats, again[1])
+	with pytest.raises(RuntimeError, match='Initial theta has wrong dimensionality.'):
+		model.update_variables_gibbs(docs, theta0[:, :-1])
+
+	# overlapping topics: averaged over many sweeps the assignments approach the variational statistics
+	K, V, B = 6, 120, 30
+	model = oracle_built.PortModel('online', V, K, 1000, .1, .2)
+	model.lambdas = np.asfortranarray(rng.gamma(.05, 1., size=(V, K)).T * 200. + .01)
+	docs = oracle_built.CSR.from_lists(random_docs(rng, B, V, 40))
+	_, sstats_vi = model.update_variables(docs, rng.gamma(100., .01, size=(B, K)).T, max_iter=200, threshold=1e-6)
+	_, sstats_gibbs = model.update_variables_gibbs(docs, num_samples=64, burn_in=16, seed=5)
+	assert np.allclose(sstats_gibbs.sum(0), sstats_vi.sum(0), rtol=0, atol=1e-6)
+	assert np.corrcoef(sstats_gibbs.ravel(), sstats_vi.ravel())[0, 1] > .9
