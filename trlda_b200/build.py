@@ -45,6 +45,7 @@ def build_library(force=False, verbose=False):
 	headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cuh', '.h'))]
 	headers.append(os.path.join(ROOT, 'include', 'trlda_b200.h'))
 	sources = [os.path.join(CSRC, 'kernels.cu'), os.path.join(CSRC, 'estep_fast.cu'), os.path.join(CSRC, 'estep_stream.cu'),
+		os.path.join(CSRC, 'estep_resident.cu'), os.path.join(CSRC, 'estep_tmem.cu'),
 		os.path.join(CSRC, 'model.cu')]
 	objects = []
 	rebuilt = False
@@ -54,7 +55,7 @@ def build_library(force=False, verbose=False):
 		if force or _newer(obj, [src] + headers):
 			_run([NVCC] + NVCC_FLAGS + ['-c', src, '-o', obj], verbose)
 			rebuilt = True
-	if rebuilt or not os.path.exists(LIB):
+	if rebuilt or _newer(LIB, objects):
 		_run([NVCC, '-shared', '-o', LIB] + objects + ['-ldl'], verbose)
 	return LIB
 

@@ -1,0 +1,713 @@
+// estep_tmem.cu — the per-document E-step (lda.cpp:174-204 of the reference), mixed mode, with the document's tile of
+// expElogbeta columns resident in TENSOR MEMORY (+ registers) for all inner iterations.
+//
+// Why TMEM.  A cfg-3 document's tile is 150 columns x 4 KB = 600 KB; the inner loop sweeps it twice per iteration, up
+// to 20 times.  Streamed from L2 (estep_stream.cu) the E-step is bound by the L2 (9.4 TB/s, 11 ms for a 20-iteration
+// E-step).  Blackwell's tensor memory — 256 KB per SM, 128 lanes x 512 32-bit columns, meant for tcgen05.mma
+// accumulators — is also a per-thread scratchpad: a warp reads 32 columns of its own 32 lanes with one tcgen05.ld
+// (SASS LDTM.x32), measured here at >= 400 B/cycle/SM with an FFMA per value (scripts/tmem_probe.cu), three times the
+// shared-memory bandwidth.  TMEM (256 values per thread at 8 warps) plus 64-128 registers per thread hold 320-384 KB
+// of tile per SM: a cluster of TWO SMs keeps a whole document on chip, all 148 SMs are used, and the per-iteration
+// exchange has a single peer.
+//
+// Decomposition.  A document is worked on by a TEAM: one group of WG warps in each of the C CTAs of a cluster; the K
+// topic rows are cut into C slabs of ROWS = 64 WG rows (K = 1000: C = 2, WG = 8).  Inside a group warp w owns 64 rows
+// and ALL columns; lane = (lr, lc) = (lane / 8, lane % 8) keeps 16 rows x 4 NU columns, column blocks u < 4 in its
+// private TMEM columns, u >= 4 in registers.
+//
+//   pass A   phi_j  = sum_k etheta_k D[k, j]       lda.cpp:183,199   in-thread over 16 rows, butterfly over lr (4 lanes)
+//   pass B   acc_k  = sum_j (c_j / phi_j) D[k, j]  lda.cpp:189-193   in-thread over 4 NU columns, butterfly over lc (8 lanes)
+//
+// Both butterflies are transposed reductions (reduce-scatter): after pass B lane l owns rows 64 w + 2 l, + 1 and
+// updates those TWO topics (gamma, exp(psi(gamma)), lda.cpp:194-197: two independent fp64 chains per lane); after pass
+// A lane l holds the warp's partial phi of columns l + 32 u.  A lane-dependent XOR permutation of the layout (slot i
+// of a lane holds row 16 lr + (i ^ 2 lc); slot (q, u) column lc + 8 (q ^ lr) + 32 u) makes the butterflies plain
+// shfl.bfly + add without selects; the inner products are packed FFMA2 (fma.rn.f32x2).
+//
+// Per inner iteration ONE exchange: the group's partial phi (summed over its warps in shared memory) and its share of
+// sum |delta gamma| go to every CTA of the cluster by st.async (DSMEM stores completing on the receiver's mbarrier);
+// all CTAs add the partials in rank order — identical bits, identical convergence decisions (lda.cpp:202) — then one
+// thread per column forms the token weight W_j = c_j / phi_j and leaves it in shared memory in the four lane
+// permutations, from where every lane fetches its 4 NU weights with NU 128-bit loads.
+//
+// The tile arrives from HBM in chunks of 32 columns through a two-slot landing ring in shared memory (cp.async.bulk per
+// column slab, issued by one lane, completing on the slot's mbarrier) and is moved to TMEM by tcgen05.st; the first two
+// chunks of a team's NEXT document are requested while the current one still iterates.
+#include "kernels.cuh"
+#include "special.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+
+namespace trlda {
+
+namespace {
+
+using u64 = unsigned long long;
+
+__device__ __forceinline__ u64 t_pack2(float lo, float hi) {
+	u64 r;
+	asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+	return r;
+}
+__device__ __forceinline__ u64 t_pack2u(uint32_t lo, uint32_t hi) {
+	u64 r;
+	asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+	return r;
+}
+__device__ __forceinline__ void t_unpack2(u64 v, float& lo, float& hi) {
+	asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 t_ffma2(u64 a, u64 b, u64 c) {
+	u64 d;
+	asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+	return d;
+}
+__device__ __forceinline__ u64 t_fmul2(u64 a, u64 b) {
+	u64 d;
+	asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+	return d;
+}
+__device__ __forceinline__ u64 t_fadd2(u64 a, u64 b) {
+	u64 d;
+	asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+	return d;
+}
+__device__ __forceinline__ u64 t_shfl_xor2(u64 v, int mask) {
+	float lo, hi;
+	t_unpack2(v, lo, hi);
+	lo = __shfl_xor_sync(0xffffffffu, lo, mask);
+	hi = __shfl_xor_sync(0xffffffffu, hi, mask);
+	return t_pack2(lo, hi);
+}
+
+__device__ __forceinline__ uint32_t t_smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint32_t t_map_to_rank(uint32_t smem_addr, int rank) {
+	uint32_t remote;
+	asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_addr), "r"(rank));
+	return remote;
+}
+
+__device__ __forceinline__ void t_mbar_wait(uint32_t bar, uint32_t parity) {
+	uint32_t done = 0;
+	while(!done)
+		asm volatile(
+			"{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+			: "=r"(done) : "r"(bar), "r"(parity) : "memory");
+}
+
+template <int GT>
+__device__ __forceinline__ void t_group_barrier(int g) {
+	if(GT == 512)
+		__syncthreads();
+	else
+		asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"(GT) : "memory");
+}
+
+// 32 consecutive TMEM columns of this thread's lane <-> 32 registers
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+	asm volatile(
+		"tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+		"%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+		: "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+		  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+		  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+		  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+		: "r"(taddr) : "memory");
+	asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+	asm volatile(
+		"tcgen05.st.sync.aligned.32x32b.x32.b32 [%32], {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+		"%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31};"
+		:: "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+		   "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+		   "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+		   "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]),
+		   "r"(taddr) : "memory");
+}
+
+
+constexpr int kTmemBlocks = 4;     // column blocks (64 values each) of a thread's tile kept in TMEM: 8 warps x 256 columns
+
+}  // namespace
+
+// shared memory of one group (bytes)
+struct TmemSmem {
+	size_t ring, red, xbuf, wperm, dl, bars, ticks, group_total;
+};
+
+__host__ __device__ constexpr TmemSmem tmem_smem_layout(int C, int NU, int WG) {
+	const int NJ = 32 * NU, ROWS = 64 * WG;
+	TmemSmem L{};
+	size_t o = 0;
+	L.ring = o; o += (size_t) 2 * 32 * ROWS * 4;                   // landing ring: 2 slots x [32 columns][ROWS]
+	L.red = o; o += (size_t) WG * NJ * 4;                          // per-warp partial phi [WG][NJ]
+	L.xbuf = o; o += C > 1 ? (size_t) 2 * C * (NJ + 4) * 4 : 0;    // incoming partials [parity][C][NJ + 4]
+	L.wperm = o; o += (size_t) 128 * NU * 4;                       // token weights in lane order [lane][NU][4]
+	L.dl = o; o += (size_t) WG * 4 + 16;                           // per-warp |delta gamma| sums
+	o = (o + 15) & ~size_t(15);
+	L.bars = o; o += 32;                                           // xbar[2], full[2]
+	L.ticks = o; o += 16 * 8;                                      // debug phase timers (TRLDA_ESTEP_TICKS=1)
+	L.group_total = (o + 127) & ~size_t(127);
+	return L;
+}
+
+template <int C, int NU, int WG>
+__global__ void __launch_bounds__(256, 1)
+k_estep_tmem(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, int64_t doc_offset, int64_t count) {
+	constexpr int G = 8 / WG;                  // groups (documents in flight) per CTA
+	constexpr int GT = 32 * WG;                // threads per group
+	constexpr int ROWS = 64 * WG;              // topic rows per CTA
+	constexpr int NJ = 32 * NU;                // column capacity
+	constexpr int XS = NJ + 4;                 // floats per rank slot of the exchange buffer (the delta sits at [NJ])
+	constexpr int UT = NU < kTmemBlocks ? NU : kTmemBlocks;   // column blocks in TMEM
+	constexpr int UR = NU - UT;                // column blocks in registers
+	constexpr int NCW = (NJ + GT - 1) / GT;    // columns per weight thread
+	constexpr TmemSmem L = tmem_smem_layout(C, NU, WG);
+	extern __shared__ __align__(128) unsigned char smem[];
+	__shared__ uint32_t tmem_base_slot;
+
+	const int tid = threadIdx.x, warp = tid >> 5;
+	const int g = tid / GT, tg = tid % GT, wg = tg >> 5, lane = tid & 31, lr = lane >> 3, lc = lane & 7;
+	unsigned char* base = smem + (size_t) g * L.group_total;
+	float* ring = reinterpret_cast<float*>(base + L.ring);
+	float* red = reinterpret_cast<float*>(base + L.red);
+	float* xbuf = reinterpret_cast<float*>(base + L.xbuf);
+	float* wperm = reinterpret_cast<float*>(base + L.wperm);
+	float* dl = reinterpret_cast<float*>(base + L.dl);
+	uint64_t* bars = reinterpret_cast<uint64_t*>(base + L.bars);
+	const uint32_t xbar_addr = t_smem_u32(bars), full_addr = t_smem_u32(bars + 2);
+	const uint32_t xbuf_addr = t_smem_u32(xbuf), ring_addr = t_smem_u32(ring);
+	long long* tk = reinterpret_cast<long long*>(base + L.ticks);
+	const bool timing = a.ticks != nullptr && tg == 0;
+	#define TRLDA_TTICK(i) if(timing) { const long long now = clock64(); tk[i] += now - tk[15]; tk[15] = now; }
+
+	int rank = 0;
+	unsigned cluster_id = blockIdx.x;
+	if(C > 1) {
+		asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+		asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(cluster_id));
+	}
+	const int n_teams = (int) (gridDim.x / C) * G;
+	const int team = (int) cluster_id * G + g;
+
+	const int K = a.K;
+	const float* __restrict__ beta = static_cast<const float*>(a.beta);
+	const int row0 = rank * ROWS;                                  // first topic row of this CTA's slab
+	const int rows_valid = max(0, min(ROWS, K - row0));
+	const uint32_t col_bytes = (uint32_t) rows_valid * 4u;
+	const int k_mine = row0 + 64 * wg + 2 * lane;                  // the two topics this lane updates: k_mine, k_mine + 1
+	const bool live = k_mine < K;                                  // K is a multiple of 4: both or none
+	double alpha_mine[2] = {0.0, 0.0};
+	if(live) {
+		alpha_mine[0] = a.alpha[k_mine];
+		alpha_mine[1] = a.alpha[k_mine + 1];
+	}
+
+	// ---- set-up: TMEM, barriers, zeroed landing ring -----------------------------------------------------------------
+	if(warp == 0) {
+		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(t_smem_u32(&tmem_base_slot)) : "memory");
+		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+	}
+	// rows beyond K of a slab are never written by the copies: they stay zero (and meet etheta = 0 anyway)
+	for(int i = tg; i < 2 * 32 * ROWS / 4; i += GT)
+		reinterpret_cast<float4*>(ring)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+	if(timing)
+		for(int i = 0; i < 16; ++i)
+			tk[i] = 0;
+	if(tg == 0) {
+		for(int i = 0; i < 4; ++i)
+			asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(xbar_addr + 8u * i));
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+	asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+	__syncthreads();
+	asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+	// this thread's private TMEM columns: lanes 32 (warp % 4) .., columns 256 (warp / 4) ..
+	const uint32_t taddr = tmem_base_slot + ((uint32_t) (32 * (warp & 3)) << 16) + (uint32_t) ((warp >> 2) * 256);
+	if(C > 1) {
+		asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+		asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+	}
+
+	// document of a work item: index, first pair, number of pairs
+	auto doc_of = [&](int item, int& d, int& begin, int& n) {
+		d = order ? order[doc_offset + item] : (int) (doc_offset + item);
+		const int64_t b = docs.doc_ptr[d];
+		begin = (int) b;
+		n = (int) (docs.doc_ptr[d + 1] - b);
+	};
+	// chunk u of a document (columns 32 u ..) into ring slot `slot`: warp 0 of the group, `ids` = word id of column 32 u + lane
+	auto issue_chunk = [&](int ids, int nv, int slot) {
+		if(lane == 0) {
+			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full_addr + 8u * slot), "r"((uint32_t) nv * col_bytes) : "memory");
+		}
+		if(col_bytes)
+			for(int l = 0; l < nv; ++l) {
+				const int w = __shfl_sync(0xffffffffu, ids, l);
+				if(lane == 0) {
+					const float* src = beta + (int64_t) w * K + row0;
+					asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+						::"r"(ring_addr + (uint32_t) (slot * 32 + l) * (ROWS * 4u)), "l"(src), "r"(col_bytes), "r"(full_addr + 8u * slot) : "memory");
+				}
+			}
+	};
+	auto chunk_cols = [](int n, int u) { return max(0, min(32, n - 32 * u)); };
+
+	uint32_t seq = 0;          // exchanges done by this team (identical in all its CTAs)
+	uint32_t cc = 0;           // chunks consumed by this group
+	int d = 0, begin = 0, n = 0, d_next = 0, begin_next = 0, n_next = 0;
+	int ids_next[2] = {0, 0};  // (warp 0 of the group) word ids of the first two chunks of the next document
+	if(team < count) {
+		doc_of(team, d_next, begin_next, n_next);
+		if(wg == 0) {
+			#pragma unroll
+			for(int u = 0; u < 2; ++u) {
+				ids_next[u] = 32 * u + lane < n_next ? docs.word_ids[begin_next + 32 * u + lane] : 0;
+				issue_chunk(ids_next[u], chunk_cols(n_next, u), u);
+			}
+		}
+	}
+
+	for(int item = team; item < count; item += n_teams) {
+		d = d_next; begin = begin_next; n = n_next;
+		const bool more = item + n_teams < count;
+		if(more)
+			doc_of(item + n_teams, d_next, begin_next, n_next);
+		int ids[NU > 2 ? NU - 2 : 1];      // (warp 0 of the group) word ids of this document's chunks 2 ..
+		if(wg == 0) {
+			#pragma unroll
+			for(int u = 2; u < NU; ++u)
+				ids[u - 2] = 32 * u + lane < n ? docs.word_ids[begin + 32 * u + lane] : 0;
+			if(more) {
+				#pragma unroll
+				for(int u = 0; u < 2; ++u)
+					ids_next[u] = 32 * u + lane < n_next ? docs.word_ids[begin_next + 32 * u + lane] : 0;
+			}
+		}
+		float cntw[NCW], Wmine[NCW];       // weight threads: count and weight of columns tg + c GT
+		#pragma unroll
+		for(int c = 0; c < NCW; ++c) {
+			const int j = tg + c * GT;
+			cntw[c] = j < n ? (float) docs.counts[begin + j] : 0.f;
+			Wmine[c] = 0.f;
+		}
+		double gam[2] = {1.0, 1.0};
+		if(live) {
+			const double2 g2 = *reinterpret_cast<const double2*>(a.gamma + (int64_t) d * K + k_mine);
+			gam[0] = g2.x;
+			gam[1] = g2.y;
+		}
+		if(timing)
+			tk[15] = clock64();
+
+		// ---- tile: landing ring -> TMEM / registers, chunk by chunk --------------------------------------------------
+		// value slot c = 4 i + q of column block u: row 16 lr + (i ^ 2 lc), column lc + 8 (q ^ lr) + 32 u
+		uint32_t Dreg[UR > 0 ? UR : 1][64];
+		#pragma unroll
+		for(int u = 0; u < NU; ++u) {
+			const uint32_t slot = cc & 1u;
+			t_mbar_wait(full_addr + 8u * slot, (cc >> 1) & 1u);
+			++cc;
+			const float* srow = ring + (size_t) slot * 32 * ROWS + 64 * wg + 16 * lr;
+			#pragma unroll
+			for(int h = 0; h < 2; ++h) {
+				uint32_t v[32];    // rows i = 8 h .. 8 h + 7
+				#pragma unroll
+				for(int q = 0; q < 4; ++q) {
+					const float* col = srow + (size_t) (lc + 8 * (q ^ lr)) * ROWS;
+					#pragma unroll
+					for(int i2 = 0; i2 < 4; ++i2) {
+						const float2 pr = *reinterpret_cast<const float2*>(col + ((8 * h + 2 * i2) ^ (2 * lc)));
+						v[4 * (2 * i2) + q] = __float_as_uint(pr.x);
+						v[4 * (2 * i2 + 1) + q] = __float_as_uint(pr.y);
+					}
+				}
+				if(u < UT)
+					tmem_st32(taddr + 64u * u + 32u * h, v);
+				else {
+					#pragma unroll
+					for(int c = 0; c < 32; ++c)
+						Dreg[u < UT ? 0 : u - UT][32 * h + c] = v[c];
+				}
+			}
+			t_group_barrier<GT>(g);                 // everybody has read the slot: it may take another chunk
+			if(wg == 0) {
+				if(u + 2 < NU)
+					issue_chunk(ids[u + 2 < NU ? u : 0], chunk_cols(n, u + 2), (int) slot);
+				else if(more)
+					issue_chunk(ids_next[u + 2 - NU], chunk_cols(n_next, u + 2 - NU), (int) slot);
+			}
+		}
+		asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+
+		double e[2];
+		float ef[2];
+		#pragma unroll
+		for(int x = 0; x < 2; ++x) {
+			e[x] = live ? exp_digamma_lean(gam[x]) : 0.0;           // lda.cpp:174
+			ef[x] = (float) e[x];
+		}
+		float delta_local = 0.f;
+		float delta_total = 0.f;
+		float W[NU][4];        // token weights of this lane's columns, slot (q, u)
+		TRLDA_TTICK(0)
+
+		// one column block of the tile: 64 values, slot c = 4 i + q
+		auto block_half = [&](int u, int h, uint32_t (&r)[32]) {
+			if(u < UT)
+				tmem_ld32(taddr + 64u * u + 32u * h, r);
+			else {
+				#pragma unroll
+				for(int c = 0; c < 32; ++c)
+					r[c] = Dreg[u < UT ? 0 : u - UT][32 * h + c];
+			}
+		};
+
+		// pass A + exchange: phi of the current etheta -> token weights of this lane's columns
+		auto pass_a = [&]() {
+			float es[16];
+			#pragma unroll
+			for(int i = 0; i < 16; ++i)
+				es[i] = __shfl_xor_sync(0xffffffffu, ef[i & 1], i >> 1);   // etheta of row 16 lr + (i ^ 2 lc)
+			u64 phi2[NU][2];
+			#pragma unroll
+			for(int u = 0; u < NU; ++u) {
+				#pragma unroll
+				for(int h = 0; h < 2; ++h) {
+					uint32_t r[32];
+					block_half(u, h, r);
+					#pragma unroll
+					for(int ii = 0; ii < 8; ++ii) {
+						const u64 e2 = t_pack2(es[8 * h + ii], es[8 * h + ii]);
+						#pragma unroll
+						for(int t = 0; t < 2; ++t) {
+							const u64 dd = t_pack2u(r[4 * ii + 2 * t], r[4 * ii + 2 * t + 1]);
+							phi2[u][t] = (h == 0 && ii == 0) ? t_fmul2(dd, e2) : t_ffma2(dd, e2, phi2[u][t]);
+						}
+					}
+				}
+			}
+			// butterfly over lr (lane bits 3, 4): slots q = 2, 3 go to lane ^ 16, then slot 1 to lane ^ 8
+			float phiP[NU];
+			u64 s2[NU];
+			#pragma unroll
+			for(int u = 0; u < NU; ++u)
+				s2[u] = t_fadd2(phi2[u][0], t_shfl_xor2(phi2[u][1], 16));
+			#pragma unroll
+			for(int u = 0; u < NU; ++u) {
+				float lo, hi;
+				t_unpack2(s2[u], lo, hi);
+				phiP[u] = lo + __shfl_xor_sync(0xffffffffu, hi, 8);
+			}
+			float dsum = delta_local;
+			#pragma unroll
+			for(int o = 16; o > 0; o >>= 1)
+				dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+			TRLDA_TTICK(3)
+			#pragma unroll
+			for(int u = 0; u < NU; ++u)
+				red[wg * NJ + lane + 32 * u] = phiP[u];
+			if(lane == 0)
+				dl[wg] = dsum;
+			t_group_barrier<GT>(g);
+			const uint32_t par = seq & 1u;
+			const float* xb = xbuf + (size_t) par * C * XS;
+			if(C > 1) {
+				const uint32_t slot = xbuf_addr + (uint32_t) ((par * C + rank) * XS) * 4u;
+				const uint32_t mbar = xbar_addr + 8u * par;
+				if(tg == GT - 1) {
+					float dt = dl[0];
+					#pragma unroll
+					for(int w = 1; w < WG; ++w)
+						dt += dl[w];
+					asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "n"(C * (NJ * 4 + 4)) : "memory");
+					#pragma unroll
+					for(int r = 0; r < C; ++r)
+						asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+							::"r"(t_map_to_rank(slot + NJ * 4u, r)), "r"(__float_as_uint(dt)), "r"(t_map_to_rank(mbar, r)) : "memory");
+				}
+				for(int j4 = tg; j4 < NJ / 4; j4 += GT) {
+					float4 s = *reinterpret_cast<const float4*>(red + 4 * j4);
+					#pragma unroll
+					for(int w = 1; w < WG; ++w) {
+						const float4 o = *reinterpret_cast<const float4*>(red + w * NJ + 4 * j4);
+						s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
+					}
+					#pragma unroll
+					for(int r = 0; r < C; ++r)
+						asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+							::"r"(t_map_to_rank(slot + 16u * (uint32_t) j4, r)), "r"(__float_as_uint(s.x)), "r"(__float_as_uint(s.y)),
+							  "r"(__float_as_uint(s.z)), "r"(__float_as_uint(s.w)), "r"(t_map_to_rank(mbar, r)) : "memory");
+				}
+				TRLDA_TTICK(4)
+				t_mbar_wait(mbar, (seq >> 1) & 1u);
+				TRLDA_TTICK(5)
+				delta_total = xb[NJ];
+				#pragma unroll
+				for(int r = 1; r < C; ++r)
+					delta_total += xb[r * XS + NJ];
+			} else {
+				delta_total = dl[0];
+				#pragma unroll
+				for(int w = 1; w < WG; ++w)
+					delta_total += dl[w];
+			}
+			// one thread per column: phi (partials added in rank / warp order: identical bits in every CTA), weight,
+			// and the weight's place in the four lane permutations [lr][lc][u][q] with q = (j / 8 % 4) ^ lr
+			#pragma unroll
+			for(int c = 0; c < NCW; ++c) {
+				const int j = tg + c * GT;
+				if(NJ % GT == 0 || j < NJ) {
+					float phi;
+					if(C > 1) {
+						phi = xb[j];
+						#pragma unroll
+						for(int r = 1; r < C; ++r)
+							phi += xb[r * XS + j];
+					} else {
+						phi = red[j];
+						#pragma unroll
+						for(int w = 1; w < WG; ++w)
+							phi += red[w * NJ + j];
+					}
+					const float wj = fminf(__fdividef(cntw[c], fmaxf(phi, 1e-37f)), 1e30f);   // lda.cpp:183,192,199
+					Wmine[c] = wj;
+					const int jc = j & 7, jq = (j >> 3) & 3, ju = j >> 5;
+					#pragma unroll
+					for(int p = 0; p < 4; ++p)
+						wperm[((p * 8 + jc) * NU + ju) * 4 + (jq ^ p)] = wj;
+				}
+			}
+			t_group_barrier<GT>(g);
+			#pragma unroll
+			for(int u = 0; u < NU; ++u) {
+				const float4 w4 = *reinterpret_cast<const float4*>(wperm + (lane * NU + u) * 4);
+				W[u][0] = w4.x; W[u][1] = w4.y; W[u][2] = w4.z; W[u][3] = w4.w;
+			}
+			++seq;
+			TRLDA_TTICK(6)
+		};
+
+		// pass B: acc of this lane's two topics = sum_j W_j D[k, j]
+		auto pass_b = [&](float (&acc)[2]) {
+			u64 part2[16];
+			#pragma unroll
+			for(int u = 0; u < NU; ++u) {
+				const u64 w2[2] = {t_pack2(W[u][0], W[u][1]), t_pack2(W[u][2], W[u][3])};
+				#pragma unroll
+				for(int h = 0; h < 2; ++h) {
+					uint32_t r[32];
+					block_half(u, h, r);
+					#pragma unroll
+					for(int ii = 0; ii < 8; ++ii)
+						#pragma unroll
+						for(int t = 0; t < 2; ++t) {
+							const u64 dd = t_pack2u(r[4 * ii + 2 * t], r[4 * ii + 2 * t + 1]);
+							part2[8 * h + ii] = (u == 0 && t == 0) ? t_fmul2(dd, w2[t]) : t_ffma2(dd, w2[t], part2[8 * h + ii]);
+						}
+				}
+			}
+			float v[16];
+			#pragma unroll
+			for(int i = 0; i < 16; ++i) {
+				float lo, hi;
+				t_unpack2(part2[i], lo, hi);
+				v[i] = lo + hi;
+			}
+			// butterfly over lc (lane bits 0-2): slots 8..15 go to lane ^ 4, then 4..7 to lane ^ 2, then 2, 3 to lane ^ 1
+			#pragma unroll
+			for(int i = 0; i < 8; ++i)
+				v[i] += __shfl_xor_sync(0xffffffffu, v[i ^ 8], 4);
+			#pragma unroll
+			for(int i = 0; i < 4; ++i)
+				v[i] += __shfl_xor_sync(0xffffffffu, v[i ^ 4], 2);
+			#pragma unroll
+			for(int i = 0; i < 2; ++i)
+				v[i] += __shfl_xor_sync(0xffffffffu, v[i ^ 2], 1);
+			acc[0] = v[0];
+			acc[1] = v[1];
+			TRLDA_TTICK(1)
+		};
+
+		pass_a();                                                   // lda.cpp:183
+		int it = 0;
+		float acc[2];
+		while(it < a.max_iter) {                                    // lda.cpp:185-204
+			pass_b(acc);
+			delta_local = 0.f;
+			#pragma unroll
+			for(int x = 0; x < 2; ++x) {
+				const double g_new = fma(e[x], (double) acc[x], alpha_mine[x]);   // lda.cpp:189-195
+				const double e_new = live ? exp_digamma_lean(g_new) : 0.0;        // lda.cpp:197
+				delta_local += live ? (float) fabs(gam[x] - g_new) : 0.f;
+				gam[x] = g_new;
+				e[x] = e_new;
+				ef[x] = (float) e_new;
+			}
+			++it;
+			TRLDA_TTICK(2)
+			pass_a();                                               // lda.cpp:199
+			if(delta_total / (float) K < (float) a.threshold)       // lda.cpp:202
+				break;
+		}
+		delta_local = 0.f;
+		pass_b(acc);                                                // row sums of this document's sufficient statistics
+		if(live) {
+			const int64_t o = (int64_t) d * K + k_mine;
+			*reinterpret_cast<double2*>(a.gamma + o) = make_double2(gam[0], gam[1]);
+			*reinterpret_cast<double2*>(a.etheta + o) = make_double2(e[0], e[1]);
+			if(a.etheta32)
+				*reinterpret_cast<float2*>(a.etheta32 + o) = make_float2(ef[0], ef[1]);
+			*reinterpret_cast<double2*>(a.doc_stat + o) = make_double2((double) acc[0] * e[0], (double) acc[1] * e[1]);
+		}
+		if(rank == 0) {
+			#pragma unroll
+			for(int c = 0; c < NCW; ++c)
+				if(tg + c * GT < n)
+					a.weight[begin + tg + c * GT] = (double) Wmine[c];
+			if(tg == 0 && a.iterations)
+				a.iterations[d] = it;
+		}
+		TRLDA_TTICK(7)
+		if(timing) {
+			tk[13] += 1;
+			tk[14] += it + 1;
+		}
+	}
+	if(timing && rank == 0 && g == 0) {
+		for(int i = 0; i < 8; ++i)
+			atomicAdd(a.ticks + i, (unsigned long long) tk[i]);
+		atomicAdd(a.ticks + 14, (unsigned long long) tk[14]);
+		atomicAdd(a.ticks + 15, (unsigned long long) tk[13]);
+	}
+	#undef TRLDA_TTICK
+	if(C > 1) {
+		// no CTA may leave while a peer can still store into its exchange buffers
+		asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+		asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+	}
+	asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+	__syncthreads();
+	if(warp == 0)
+		asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base_slot) : "memory");
+}
+
+// ---- host side -------------------------------------------------------------------------------------------------
+
+namespace {
+
+struct TmemKernel {
+	const void* fn;
+	int C, NU, WG;
+	size_t smem;
+	int max_clusters;     // co-resident clusters (persistent grid), 0 = not yet known
+};
+
+template <int C, int NU, int WG>
+TmemKernel* tmem_kernel() {
+	static TmemKernel k = [] {
+		TmemKernel r{};
+		r.fn = reinterpret_cast<const void*>(&k_estep_tmem<C, NU, WG>);
+		r.C = C; r.NU = NU; r.WG = WG;
+		r.smem = tmem_smem_layout(C, NU, WG).group_total * (8 / WG);
+		return r;
+	}();
+	return &k;
+}
+
+// cluster size and group width for K topics: ROWS = 64 WG rows per CTA, C CTAs per document
+template <int NU>
+TmemKernel* tmem_pick(int K) {
+	if(K <= 128)
+		return tmem_kernel<1, NU, 2>();
+	if(K <= 256)
+		return tmem_kernel<1, NU, 4>();
+	if(K <= 512)
+		return tmem_kernel<1, NU, 8>();
+	if(K <= 1024)
+		return tmem_kernel<2, NU, 8>();
+	if(K <= 2048)
+		return tmem_kernel<4, NU, 8>();
+	return nullptr;
+}
+
+TmemKernel* tmem_select(int K, int n_max) {
+	if(n_max <= 64)
+		return tmem_pick<2>(K);
+	if(n_max <= 128)
+		return tmem_pick<4>(K);
+	if(n_max <= 160)
+		return tmem_pick<5>(K);
+	if(n_max <= 192)
+		return tmem_pick<6>(K);
+	return nullptr;
+}
+
+}  // namespace
+
+// longest document (pairs) the TMEM tile covers
+int tmem_estep_max_len() { return 192; }
+
+bool tmem_estep_applicable(int K, int elem_size) {
+	if(elem_size != 4 || K % 4 != 0 || K < 1)
+		return false;
+	return tmem_select(K, 192) != nullptr;
+}
+
+// runs documents order[offset .. offset + count), all of at most n_max <= tmem_estep_max_len() pairs
+int launch_estep_tmem(const EStepArgs& args, const DeviceDocs& docs, const int32_t* order, int64_t offset,
+                      int64_t count, int n_max, cudaStream_t s) {
+	if(count == 0)
+		return 0;
+	TmemKernel* k = tmem_select(args.K, n_max);
+	if(!k)
+		return -1;
+	const int C = k->C, G = 8 / k->WG;
+	cudaLaunchConfig_t cfg = {};
+	cfg.blockDim = dim3(256);
+	cfg.dynamicSmemBytes = k->smem;
+	cfg.stream = s;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeClusterDimension;
+	attr[0].val.clusterDim.x = C;
+	attr[0].val.clusterDim.y = 1;
+	attr[0].val.clusterDim.z = 1;
+	cfg.attrs = attr;
+	cfg.numAttrs = C > 1 ? 1 : 0;
+	if(k->max_clusters == 0) {
+		if(cudaFuncSetAttribute(k->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) k->smem) != cudaSuccess)
+			return -1;
+		int n = 0;
+		if(C > 1) {
+			cfg.gridDim = dim3(C);
+			if(cudaOccupancyMaxActiveClusters(&n, k->fn, &cfg) != cudaSuccess || n < 1) {
+				cudaGetLastError();
+				return -1;
+			}
+		} else {
+			int dev = 0;
+			cudaGetDevice(&dev);
+			cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);     // one CTA per SM: it owns the SM's TMEM
+		}
+		if(const char* e = getenv("TRLDA_TMEM_CLUSTERS"))
+			if(atoi(e) > 0)
+				n = std::min(n, atoi(e));
+		k->max_clusters = n;
+		if(getenv("TRLDA_RESIDENT_VERBOSE"))
+			fprintf(stderr, "[trlda] k_estep_tmem<C=%d, NU=%d, WG=%d>: %zu B shared memory, %d co-resident clusters\n",
+			        C, k->NU, k->WG, k->smem, n);
+	}
+	const int64_t teams_needed = (count + G - 1) / G;
+	const int clusters = (int) std::min<int64_t>(k->max_clusters, teams_needed);
+	cfg.gridDim = dim3((unsigned) (clusters * C));
+	void* params[] = {(void*) &args, (void*) &docs, (void*) &order, (void*) &offset, (void*) &count};
+	return cudaLaunchKernelExC(&cfg, k->fn, params) == cudaSuccess ? 0 : -1;
+}
+
+}  // namespace trlda

@@ -205,6 +205,9 @@ struct trlda_model {
 	// shared-memory tile is sized for the bucket's longest document
 	struct Bucket { int64_t offset, count; int n_max; };
 	std::vector<Bucket> buckets;
+	// documents longer than 192 / 160 / 128 / 64 pairs (prefix lengths of the length-sorted order): the cuts between
+	// the register-tile shapes of the resident E-step kernel
+	int64_t len_gt[4] = {0, 0, 0, 0};
 	bool force_generic = false;
 	// parked resident minibatches (trlda_upload_docs_slot / trlda_select_docs): the live buffers are swapped with a slot
 	struct DocSlot {
@@ -212,6 +215,7 @@ struct trlda_model {
 		DeviceDocs docs;
 		DevBuf b_doc_ptr, b_word_ids, b_counts, b_word_ptr, b_tok_doc, b_tok_src, b_order;
 		std::vector<Bucket> buckets;
+		int64_t len_gt[4] = {0, 0, 0, 0};
 		int64_t docs_total_count = 0, global_B = 0;
 	};
 	std::vector<DocSlot> slots;
@@ -226,6 +230,8 @@ struct trlda_model {
 	cudaStream_t aux[kAuxStreams] = {nullptr, nullptr, nullptr};
 	cudaEvent_t fork_event = nullptr, join_event[kAuxStreams] = {nullptr, nullptr, nullptr};
 	bool concurrent_buckets = true;
+	bool tmem_mode = true;       // TRLDA_ESTEP_TMEM=0: never use the tensor-memory-resident kernel (mixed mode)
+	bool resident_mode = true;   // TRLDA_ESTEP_RESIDENT=0: never use the register-resident kernel (mixed mode)
 	int stream_mode = 2;   // TRLDA_ESTEP_STREAM: 0 never use the streaming kernel, 1 only for warm-started E-steps, 2 always (default)
 	DevBuf ticks;    // debug phase timers of the fast E-step kernel (TRLDA_ESTEP_TICKS=1)
 	PinnedBuf staging, readback;
@@ -426,9 +432,30 @@ int prepare_beta(trlda_model* m, bool want_psi_partials = false) {
 	return check_launch(m, "beta_prep");
 }
 
+// exchanges the live minibatch state with a parking slot (pointer swaps only)
+void swap_with_slot(trlda_model* m, trlda_model::DocSlot& slot) {
+	std::swap(m->docs, slot.docs);
+	std::swap(m->b_doc_ptr, slot.b_doc_ptr);
+	std::swap(m->b_word_ids, slot.b_word_ids);
+	std::swap(m->b_counts, slot.b_counts);
+	std::swap(m->b_word_ptr, slot.b_word_ptr);
+	std::swap(m->b_tok_doc, slot.b_tok_doc);
+	std::swap(m->b_tok_src, slot.b_tok_src);
+	std::swap(m->b_order, slot.b_order);
+	std::swap(m->buckets, slot.buckets);
+	std::swap(m->len_gt, slot.len_gt);
+	std::swap(m->docs_total_count, slot.docs_total_count);
+	std::swap(m->global_B, slot.global_B);
+}
+
 // ---- minibatch upload: CSR + word-sorted token list ---------------------------------------------------------------
 int upload_docs(trlda_model* m, const trlda_docs* docs) {
 	TRY(set_device(m));
+	// the live buffers may belong to a parked minibatch (trlda_select_docs): hand them back before overwriting
+	if(m->live_slot >= 0) {
+		swap_with_slot(m, m->slots[m->live_slot]);
+		m->live_slot = -1;
+	}
 	if(!docs || docs->num_docs < 0 || (docs->num_docs > 0 && !docs->doc_ptr))
 		return fail(m, TRLDA_ERR_ARG, "Documents must be given in CSR form.");
 	const int64_t B = docs->num_docs;
@@ -472,12 +499,19 @@ int upload_docs(trlda_model* m, const trlda_docs* docs) {
 		s_ptr[0] = 0;
 	int n_max = 0;
 	int64_t total_count = 0;
+	int64_t len_gt[4] = {0, 0, 0, 0};
 	for(int64_t d = 0; d < B; ++d) {
 		const int64_t n = s_ptr[d + 1] - s_ptr[d];
 		if(n < 0)
 			return fail(m, TRLDA_ERR_ARG, "Document offsets must be non-decreasing.");
 		n_max = std::max<int64_t>(n_max, n);
+		len_gt[0] += n > 192;
+		len_gt[1] += n > 160;
+		len_gt[2] += n > 128;
+		len_gt[3] += n > 64;
 	}
+	for(int i = 0; i < 4; ++i)
+		m->len_gt[i] = len_gt[i];
 	// copy the id / count arrays into the pinned staging buffer (parallel slices), summing the counts and checking
 	// the id range on the way.  The word-sorted token list is built later, by ensure_csc(), right before the
 	// first kernel that needs it — by then the device is busy with the first E-step and the host work is hidden.
@@ -656,6 +690,54 @@ int run_estep(trlda_model* m, GammaSource src, const double* host_gamma, int max
 	// serves the re-sweeps); the cluster kernels remain for shapes it does not cover (K too large for the per-lane
 	// register tile, unaligned K, very long documents)
 	const bool warm = src == GAMMA_KEEP;
+	// Mixed mode: the register-resident cluster kernel (estep_resident.cu).  The documents are sorted by length, longest
+	// first: [0, len_gt[0]) do not fit the register tile and go to the streaming kernel, the rest is cut by tile shape
+	// (192 / 160 / 128 / 64 columns); a cut that would leave fewer than 64 documents joins the wider shape before it.
+	if(!m->force_generic && m->docs.B > 0 && m->resident_mode && resident_estep_applicable(m->K, m->beta_elem) &&
+	   (m->len_gt[0] == 0 || stream_estep_applicable(m->K, m->docs.n_max, m->beta_elem, m->smem_optin))) {
+		const int64_t B = m->docs.B;
+		const int64_t cut[5] = {m->len_gt[0], m->len_gt[1], m->len_gt[2], m->len_gt[3], B};
+		const int cap[5] = {0, 192, 160, 128, 64};
+		bool ok = true;
+		if(cut[0] > 0) {
+			Launch l(m, KK_ESTEP);
+			launch_estep_stream(a, m->docs, m->b_order.as<int32_t>(), 0, cut[0], m->docs.n_max, m->beta_elem, !warm, m->stream);
+		}
+		struct Range { int64_t begin, end; int shape; };
+		Range pending{cut[0], cut[0], 0};
+		const bool tmem = m->tmem_mode && tmem_estep_applicable(m->K, m->beta_elem);
+		auto flush = [&]() {
+			if(pending.end > pending.begin && ok) {
+				Launch l(m, KK_ESTEP);
+				// tile in tensor memory (documents of up to 160 pairs), else in registers
+				if(tmem && pending.shape <= tmem_estep_max_len())
+					ok = launch_estep_tmem(a, m->docs, m->b_order.as<int32_t>(), pending.begin, pending.end - pending.begin,
+					                       pending.shape, m->stream) == 0;
+				else
+					ok = launch_estep_resident(a, m->docs, m->b_order.as<int32_t>(), pending.begin, pending.end - pending.begin,
+					                           pending.shape, m->stream) == 0;
+			}
+		};
+		for(int i = 1; i < 5; ++i) {
+			if(cut[i] <= cut[i - 1])
+				continue;
+			if(pending.end == pending.begin)
+				pending = {cut[i - 1], cut[i], cap[i]};
+			else if(cut[i] - cut[i - 1] < 64 && !(tmem && pending.shape > tmem_estep_max_len()))
+				pending.end = cut[i];                    // merged: the wider shape covers a few shorter documents
+			else {
+				flush();
+				pending = {cut[i - 1], cut[i], cap[i]};
+			}
+		}
+		flush();
+		if(ok) {
+			m->gamma_valid = true;
+			m->stats.estep_docs = m->docs.B;
+			return check_launch(m, "estep_resident");
+		}
+		return fail(m, TRLDA_ERR_CUDA, "The resident E-step kernel could not be launched.");
+	}
 	if(!m->force_generic && m->docs.B > 0 && (m->stream_mode == 2 || (m->stream_mode == 1 && warm)) &&
 	   stream_estep_applicable(m->K, m->docs.n_max, m->beta_elem, m->smem_optin)) {
 		{
@@ -1450,6 +1532,10 @@ int trlda_create(int kind, int num_words, int num_topics, int64_t num_documents,
 	configure_estep_fast(m->smem_optin);
 	if(const char* sm = getenv("TRLDA_ESTEP_STREAM"))
 		m->stream_mode = atoi(sm);
+	if(const char* rm = getenv("TRLDA_ESTEP_RESIDENT"))
+		m->resident_mode = atoi(rm) != 0;
+	if(const char* tm = getenv("TRLDA_ESTEP_TMEM"))
+		m->tmem_mode = atoi(tm) != 0;
 	if(const char* cb = getenv("TRLDA_CONCURRENT_BUCKETS"))
 		m->concurrent_buckets = atoi(cb) != 0;
 	cudaEventCreateWithFlags(&m->fork_event, cudaEventDisableTiming);
@@ -1492,6 +1578,14 @@ void trlda_destroy(trlda_model* m) {
 		                                     "pass1", "gamma/psi/delta", "pass2+push", "exchange+W", "results+doc_stat", "-"};
 		static const char* stream_names[10] = {"document setup", "sweep (stream columns)", "fold partial sums", "cluster exchange",
 		                                       "gamma/psi update + results", "convergence test", "-", "-", "-", "-"};
+		static const char* resident_names[8] = {"tile wait + registers + psi0", "pass B (acc) + butterfly", "gamma/psi update", "pass A (phi) + butterflies",
+		                                        "fold in smem + barrier + send", "exchange wait", "sum ranks + W", "results"};
+		if(m->resident_mode && m->beta_elem == 4 && resident_estep_applicable(m->K, m->beta_elem)) {
+			fprintf(stderr, "[trlda] resident E-step phase timers (one thread of rank 0, group 0 per cluster): %llu documents, %llu exchanges\n", t[15], t[14]);
+			for(int i = 0; i < 8; ++i)
+				fprintf(stderr, "[trlda]   %-30s %10.0f cycles/doc %8.0f cycles/exchange\n", resident_names[i],
+				        t[15] ? (double) t[i] / (double) t[15] : 0.0, t[14] ? (double) t[i] / (double) t[14] : 0.0);
+		}
 		const bool streamed = m->stream_mode != 0;
 		fprintf(stderr, "[trlda] %s E-step phase timers: %llu documents, %llu %s\n", streamed ? "streaming" : "fast", t[15], t[14],
 		        streamed ? "sweeps" : "inner iterations");
@@ -1633,22 +1727,6 @@ int trlda_upload_docs(trlda_model* m, const trlda_docs* docs) {
 	return upload_docs(m, docs);
 }
 
-namespace {
-// exchanges the live minibatch state with a parking slot (pointer swaps only)
-void swap_with_slot(trlda_model* m, trlda_model::DocSlot& slot) {
-	std::swap(m->docs, slot.docs);
-	std::swap(m->b_doc_ptr, slot.b_doc_ptr);
-	std::swap(m->b_word_ids, slot.b_word_ids);
-	std::swap(m->b_counts, slot.b_counts);
-	std::swap(m->b_word_ptr, slot.b_word_ptr);
-	std::swap(m->b_tok_doc, slot.b_tok_doc);
-	std::swap(m->b_tok_src, slot.b_tok_src);
-	std::swap(m->b_order, slot.b_order);
-	std::swap(m->buckets, slot.buckets);
-	std::swap(m->docs_total_count, slot.docs_total_count);
-	std::swap(m->global_B, slot.global_B);
-}
-}  // namespace
 
 int trlda_upload_docs_slot(trlda_model* m, const trlda_docs* docs, int slot) {
 	if(slot < 0 || slot >= 64)
