@@ -1,8 +1,8 @@
-"""E-step kernels on the cfg-3 shape: register-resident cluster kernel against the streaming kernel.
+"""E-step kernels on the cfg-3 shape: tensor-memory-resident cluster kernel against the streaming kernel.
 
-One cold E-step (fresh gamma, 20 inner iterations) and one warm E-step (restart from the converged gamma), each run
-with TRLDA_ESTEP_RESIDENT=1 and =0; prints the E-step kernel time and the largest relative difference of gamma
-between the two.  The switch is read when a model is created, so every leg builds its own model."""
+One cold E-step (fresh gamma, 20 inner iterations), one warm E-step (restart from the converged gamma) and one with a
+single inner iteration, each run with TRLDA_ESTEP_TMEM=1 and =0; prints the E-step kernel time and the largest relative
+difference of gamma between the two.  The switch is read when a model is created, so every leg builds its own model."""
 import os
 import sys
 import time
@@ -20,11 +20,11 @@ g0 = gamma_matrix(K, B, 3003)
 lam0 = gamma_matrix(K, V, 2003)
 
 
-MODES = {'stream': ('0', '0'), 'resident': ('1', '0'), 'tmem': ('1', '1')}
+MODES = {'stream': '0', 'tmem': '1'}
 
 
 def run(mode, gamma, max_iter, reps=3):
-	os.environ['TRLDA_ESTEP_RESIDENT'], os.environ['TRLDA_ESTEP_TMEM'] = MODES[mode]
+	os.environ['TRLDA_ESTEP_TMEM'] = MODES[mode]
 	m = capi.Model('online', V, K, 1000000, .1, .2, precision='mixed')
 	m.lambdas = lam0
 	m.update_variables(docs, gamma, max_iter=max_iter, want_sstats=False)     # warm-up (beta-prep, allocations)
@@ -46,13 +46,12 @@ for label, gamma, it in (('cold', g0, 20), ('warm', None, 20), ('one', g0, 1)):
 	if gamma is None:
 		gamma = results[('cold', 'stream')][0] if ('cold', 'stream') in results else g0
 		# converge further so that the warm start stops after one or two iterations
-		os.environ['TRLDA_ESTEP_RESIDENT'] = '0'
 		os.environ['TRLDA_ESTEP_TMEM'] = '0'
 		m = capi.Model('online', V, K, 1000000, .1, .2, precision='mixed')
 		m.lambdas = lam0
 		gamma, _ = m.update_variables(docs, gamma, max_iter=100, want_sstats=False)
 		m.close()
-	for mode in os.environ.get('MODES', 'stream,resident,tmem').split(','):
+	for mode in os.environ.get('MODES', 'stream,tmem').split(','):
 		try:
 			results[(label, mode)] = run(mode, gamma, it)
 		except Exception as e:            # noqa: BLE001

@@ -26,7 +26,7 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
 }
 
 // NW warps; every warp owns 512 * 4 / NW columns of its lane quarter (NW = 4: all 512; 8: 256; 16: 128)
-template <int NW>
+template <int NW, int MODE>
 __global__ void __launch_bounds__(NW * 32, 1) k_tmem(int iters, unsigned long long* cycles, uint32_t* check, float* sink) {
 	__shared__ uint32_t tmem_base;
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -71,10 +71,30 @@ __global__ void __launch_bounds__(NW * 32, 1) k_tmem(int iters, unsigned long lo
 			tmem_ld32(mine + c, v0);
 			tmem_ld32(mine + c + 32, v1);
 			asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-			#pragma unroll
-			for(int i = 0; i < 32; ++i) {
-				acc[i & 3] = fmaf(__uint_as_float(v0[i]), 1.0001f, acc[i & 3]);
-				acc[(i + 2) & 3] = fmaf(__uint_as_float(v1[i]), 0.9999f, acc[(i + 2) & 3]);
+			if(MODE == 0) {
+				#pragma unroll
+				for(int i = 0; i < 32; ++i) {
+					acc[i & 3] = fmaf(__uint_as_float(v0[i]), 1.0001f, acc[i & 3]);
+					acc[(i + 2) & 3] = fmaf(__uint_as_float(v1[i]), 0.9999f, acc[(i + 2) & 3]);
+				}
+			} else if(MODE == 1) {
+				#pragma unroll
+				for(int i = 0; i < 32; i += 2) {
+					unsigned long long a0 = ((unsigned long long) v0[i + 1] << 32) | v0[i], a1 = ((unsigned long long) v1[i + 1] << 32) | v1[i];
+					unsigned long long c0 = ((unsigned long long) __float_as_uint(acc[1]) << 32) | __float_as_uint(acc[0]);
+					unsigned long long c1 = ((unsigned long long) __float_as_uint(acc[3]) << 32) | __float_as_uint(acc[2]);
+					const unsigned long long w = 0x3f8003473f800347ull;
+					asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c0) : "l"(a0), "l"(w));
+					asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c1) : "l"(a1), "l"(w));
+					acc[0] = __uint_as_float((unsigned) c0); acc[1] = __uint_as_float((unsigned) (c0 >> 32));
+					acc[2] = __uint_as_float((unsigned) c1); acc[3] = __uint_as_float((unsigned) (c1 >> 32));
+				}
+			} else {
+				unsigned x = 0;
+				#pragma unroll
+				for(int i = 0; i < 32; i += 4)
+					x ^= (v0[i] ^ v0[i + 1]) ^ (v0[i + 2] ^ v0[i + 3]) ^ (v1[i] ^ v1[i + 1]) ^ (v1[i + 2] ^ v1[i + 3]);
+				acc[0] += __uint_as_float(x & 0x3fffffff);
 			}
 		}
 	}
@@ -87,14 +107,14 @@ __global__ void __launch_bounds__(NW * 32, 1) k_tmem(int iters, unsigned long lo
 		asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
 }
 
-template <int NW>
+template <int NW, int MODE>
 void run(unsigned long long* cycles, uint32_t* check, float* sink) {
 	const int iters = 200;
 	cudaMemset(check, 0, 4);
 	cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-	k_tmem<NW><<<148, NW * 32>>>(2, cycles, check, sink);
+	k_tmem<NW, MODE><<<148, NW * 32>>>(2, cycles, check, sink);
 	cudaEventRecord(e0);
-	k_tmem<NW><<<148, NW * 32>>>(iters, cycles, check, sink);
+	k_tmem<NW, MODE><<<148, NW * 32>>>(iters, cycles, check, sink);
 	cudaEventRecord(e1);
 	cudaError_t err = cudaEventSynchronize(e1);
 	float ms; cudaEventElapsedTime(&ms, e0, e1);
@@ -102,16 +122,22 @@ void run(unsigned long long* cycles, uint32_t* check, float* sink) {
 	cudaMemcpy(&cyc, cycles, 8, cudaMemcpyDeviceToHost);
 	cudaMemcpy(&bad, check, 4, cudaMemcpyDeviceToHost);
 	const double bytes = 256.0 * 1024 * iters;      // per SM
-	printf("warps=%2d: %s, mismatches %u, %.1f B/cycle/SM (clock64), whole kernel %.3f ms -> %.1f TB/s chip\n", NW,
+	printf("mode %d (0: FFMA per value, 1: FFMA2 per pair, 2: XOR only) warps=%2d: %s, mismatches %u, %.1f B/cycle/SM (clock64), whole kernel %.3f ms -> %.1f TB/s chip\n", MODE, NW,
 	       cudaGetErrorString(err), bad, bytes / (double) cyc, ms, bytes * 148 / (ms * 1e-3) / 1e12);
 }
 
 int main() {
 	unsigned long long* cycles; uint32_t* check; float* sink;
 	cudaMalloc(&cycles, 8); cudaMalloc(&check, 4); cudaMalloc(&sink, 148 * 512 * 4);
-	run<4>(cycles, check, sink);
-	run<8>(cycles, check, sink);
-	run<16>(cycles, check, sink);
+	run<4, 0>(cycles, check, sink);
+	run<8, 0>(cycles, check, sink);
+	run<16, 0>(cycles, check, sink);
+	run<4, 1>(cycles, check, sink);
+	run<8, 1>(cycles, check, sink);
+	run<16, 1>(cycles, check, sink);
+	run<4, 2>(cycles, check, sink);
+	run<8, 2>(cycles, check, sink);
+	run<16, 2>(cycles, check, sink);
 	printf("%s\n", cudaGetErrorString(cudaGetLastError()));
 	return 0;
 }

@@ -30,9 +30,9 @@
 // thread per column forms the token weight W_j = c_j / phi_j and leaves it in shared memory in the four lane
 // permutations, from where every lane fetches its 4 NU weights with NU 128-bit loads.
 //
-// The tile arrives from HBM in chunks of 32 columns through a two-slot landing ring in shared memory (cp.async.bulk per
-// column slab, issued by one lane, completing on the slot's mbarrier) and is moved to TMEM by tcgen05.st; the first two
-// chunks of a team's NEXT document are requested while the current one still iterates.
+// The tile arrives from HBM in chunks of 32 columns through a three-slot landing ring in shared memory (cp.async.bulk per
+// column slab, completing on the slot's mbarrier) and is moved to TMEM by tcgen05.st; the first three chunks of a team's
+// NEXT document are requested while the current one still iterates.
 #include "kernels.cuh"
 #include "special.cuh"
 
@@ -143,13 +143,14 @@ __host__ __device__ constexpr TmemSmem tmem_smem_layout(int C, int NU, int WG) {
 	const int NJ = 32 * NU, ROWS = 64 * WG;
 	TmemSmem L{};
 	size_t o = 0;
-	L.ring = o; o += (size_t) 2 * 32 * ROWS * 4;                   // landing ring: 2 slots x [32 columns][ROWS]
+	const int NS = NU < 3 ? NU : 3;
+	L.ring = o; o += (size_t) NS * 32 * ROWS * 4;                  // landing ring: NS slots x [32 columns][ROWS]
 	L.red = o; o += (size_t) WG * NJ * 4;                          // per-warp partial phi [WG][NJ]
 	L.xbuf = o; o += C > 1 ? (size_t) 2 * C * (NJ + 4) * 4 : 0;    // incoming partials [parity][C][NJ + 4]
 	L.wperm = o; o += (size_t) 128 * NU * 4;                       // token weights in lane order [lane][NU][4]
 	L.dl = o; o += (size_t) WG * 4 + 16;                           // per-warp |delta gamma| sums
 	o = (o + 15) & ~size_t(15);
-	L.bars = o; o += 32;                                           // xbar[2], full[2]
+	L.bars = o; o += 40;                                           // xbar[2], full[3]
 	L.ticks = o; o += 16 * 8;                                      // debug phase timers (TRLDA_ESTEP_TICKS=1)
 	L.group_total = (o + 127) & ~size_t(127);
 	return L;
@@ -166,6 +167,7 @@ k_estep_tmem(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, in
 	constexpr int UT = NU < kTmemBlocks ? NU : kTmemBlocks;   // column blocks in TMEM
 	constexpr int UR = NU - UT;                // column blocks in registers
 	constexpr int NCW = (NJ + GT - 1) / GT;    // columns per weight thread
+	constexpr int NS = NU < 3 ? NU : 3;        // landing slots (chunks of 32 columns in flight)
 	constexpr TmemSmem L = tmem_smem_layout(C, NU, WG);
 	extern __shared__ __align__(128) unsigned char smem[];
 	__shared__ uint32_t tmem_base_slot;
@@ -213,13 +215,13 @@ k_estep_tmem(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, in
 		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
 	}
 	// rows beyond K of a slab are never written by the copies: they stay zero (and meet etheta = 0 anyway)
-	for(int i = tg; i < 2 * 32 * ROWS / 4; i += GT)
+	for(int i = tg; i < NS * 32 * ROWS / 4; i += GT)
 		reinterpret_cast<float4*>(ring)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 	if(timing)
 		for(int i = 0; i < 16; ++i)
 			tk[i] = 0;
 	if(tg == 0) {
-		for(int i = 0; i < 4; ++i)
+		for(int i = 0; i < 5; ++i)
 			asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(xbar_addr + 8u * i));
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
@@ -241,14 +243,15 @@ k_estep_tmem(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, in
 		begin = (int) b;
 		n = (int) (docs.doc_ptr[d + 1] - b);
 	};
-	// chunk u of a document (columns 32 u ..) into ring slot `slot`: warp 0 of the group, `ids` = word id of column 32 u + lane
+	// chunk u of a document (columns 32 u ..) into ring slot `slot`: `ids` = word id of column 32 u + lane (every warp of
+	// the group holds them); warp wg issues the columns wg, wg + WG, ..., one lane each copy
 	auto issue_chunk = [&](int ids, int nv, int slot) {
-		if(lane == 0) {
-			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+		if(tg == 0)
 			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full_addr + 8u * slot), "r"((uint32_t) nv * col_bytes) : "memory");
-		}
+		if(lane == 0)
+			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 		if(col_bytes)
-			for(int l = 0; l < nv; ++l) {
+			for(int l = wg; l < nv; l += WG) {
 				const int w = __shfl_sync(0xffffffffu, ids, l);
 				if(lane == 0) {
 					const float* src = beta + (int64_t) w * K + row0;
@@ -262,15 +265,16 @@ k_estep_tmem(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, in
 	uint32_t seq = 0;          // exchanges done by this team (identical in all its CTAs)
 	uint32_t cc = 0;           // chunks consumed by this group
 	int d = 0, begin = 0, n = 0, d_next = 0, begin_next = 0, n_next = 0;
-	int ids_next[2] = {0, 0};  // (warp 0 of the group) word ids of the first two chunks of the next document
+	int ids_next[NS];          // word ids (column 32 u + lane) of the first NS chunks of the next document
+	#pragma unroll
+	for(int u = 0; u < NS; ++u)
+		ids_next[u] = 0;
 	if(team < count) {
 		doc_of(team, d_next, begin_next, n_next);
-		if(wg == 0) {
-			#pragma unroll
-			for(int u = 0; u < 2; ++u) {
-				ids_next[u] = 32 * u + lane < n_next ? docs.word_ids[begin_next + 32 * u + lane] : 0;
-				issue_chunk(ids_next[u], chunk_cols(n_next, u), u);
-			}
+		#pragma unroll
+		for(int u = 0; u < NS; ++u) {
+			ids_next[u] = 32 * u + lane < n_next ? docs.word_ids[begin_next + 32 * u + lane] : 0;
+			issue_chunk(ids_next[u], chunk_cols(n_next, u), u);
 		}
 	}
 
@@ -279,16 +283,14 @@ k_estep_tmem(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, in
 		const bool more = item + n_teams < count;
 		if(more)
 			doc_of(item + n_teams, d_next, begin_next, n_next);
-		int ids[NU > 2 ? NU - 2 : 1];      // (warp 0 of the group) word ids of this document's chunks 2 ..
-		if(wg == 0) {
+		int ids[NU > NS ? NU - NS : 1];    // word ids of this document's chunks NS ..
+		#pragma unroll
+		for(int u = NS; u < NU; ++u)
+			ids[u - NS] = 32 * u + lane < n ? docs.word_ids[begin + 32 * u + lane] : 0;
+		if(more) {
 			#pragma unroll
-			for(int u = 2; u < NU; ++u)
-				ids[u - 2] = 32 * u + lane < n ? docs.word_ids[begin + 32 * u + lane] : 0;
-			if(more) {
-				#pragma unroll
-				for(int u = 0; u < 2; ++u)
-					ids_next[u] = 32 * u + lane < n_next ? docs.word_ids[begin_next + 32 * u + lane] : 0;
-			}
+			for(int u = 0; u < NS; ++u)
+				ids_next[u] = 32 * u + lane < n_next ? docs.word_ids[begin_next + 32 * u + lane] : 0;
 		}
 		float cntw[NCW], Wmine[NCW];       // weight threads: count and weight of columns tg + c GT
 		#pragma unroll
@@ -311,8 +313,8 @@ k_estep_tmem(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, in
 		uint32_t Dreg[UR > 0 ? UR : 1][64];
 		#pragma unroll
 		for(int u = 0; u < NU; ++u) {
-			const uint32_t slot = cc & 1u;
-			t_mbar_wait(full_addr + 8u * slot, (cc >> 1) & 1u);
+			const uint32_t slot = cc % NS;
+			t_mbar_wait(full_addr + 8u * slot, (cc / NS) & 1u);
 			++cc;
 			const float* srow = ring + (size_t) slot * 32 * ROWS + 64 * wg + 16 * lr;
 			#pragma unroll
@@ -337,12 +339,10 @@ k_estep_tmem(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, in
 				}
 			}
 			t_group_barrier<GT>(g);                 // everybody has read the slot: it may take another chunk
-			if(wg == 0) {
-				if(u + 2 < NU)
-					issue_chunk(ids[u + 2 < NU ? u : 0], chunk_cols(n, u + 2), (int) slot);
-				else if(more)
-					issue_chunk(ids_next[u + 2 - NU], chunk_cols(n_next, u + 2 - NU), (int) slot);
-			}
+			if(u + NS < NU)
+				issue_chunk(ids[u + NS < NU ? u : 0], chunk_cols(n, u + NS), (int) slot);
+			else if(more)
+				issue_chunk(ids_next[u + NS - NU < NS ? u + NS - NU : 0], chunk_cols(n_next, u + NS - NU), (int) slot);
 		}
 		asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 
@@ -624,6 +624,12 @@ TmemKernel* tmem_kernel() {
 // cluster size and group width for K topics: ROWS = 64 WG rows per CTA, C CTAs per document
 template <int NU>
 TmemKernel* tmem_pick(int K) {
+	// TRLDA_TMEM_WG = 4 / 2: narrower groups, more CTAs per document (experiments: two / four documents per SM)
+	static const int forced = [] { const char* e = getenv("TRLDA_TMEM_WG"); return e ? atoi(e) : 0; }();
+	if(forced == 4 && K > 512 && K <= 1024)
+		return tmem_kernel<4, NU, 4>();
+	if(forced == 2 && K > 512 && K <= 1024)
+		return tmem_kernel<8, NU, 2>();
 	if(K <= 128)
 		return tmem_kernel<1, NU, 2>();
 	if(K <= 256)
@@ -709,5 +715,6 @@ int launch_estep_tmem(const EStepArgs& args, const DeviceDocs& docs, const int32
 	void* params[] = {(void*) &args, (void*) &docs, (void*) &order, (void*) &offset, (void*) &count};
 	return cudaLaunchKernelExC(&cfg, k->fn, params) == cudaSuccess ? 0 : -1;
 }
+
 
 }  // namespace trlda

@@ -104,15 +104,8 @@ bool stream_estep_applicable(int K, int n_max, int elem_size, int smem_optin);
 void launch_estep_stream(const EStepArgs& args, const DeviceDocs& docs, const int32_t* order, int64_t offset,
                          int64_t count, int n_max, int elem_size, bool cold, cudaStream_t s);
 
-// register-resident kernel for the mixed mode (estep_resident.cu): a cluster of CTAs per document team keeps the
-// document's float32 tile in registers for all inner iterations; documents of up to resident_estep_max_len() pairs
-bool resident_estep_applicable(int K, int elem_size);
-int resident_estep_max_len();
-int launch_estep_resident(const EStepArgs& args, const DeviceDocs& docs, const int32_t* order, int64_t offset,
-                          int64_t count, int n_max, cudaStream_t s);
-
-// tensor-memory-resident kernel for the mixed mode (estep_tmem.cu): like the register-resident one, but the tile lives
-// in the SM's tensor memory, so that 16 warps (2-4 documents) share an SM; documents of up to tmem_estep_max_len() pairs
+// tensor-memory-resident kernel for the mixed mode (estep_tmem.cu): a cluster of CTAs keeps a document's float32 tile
+// in tensor memory (+ registers) for all inner iterations; documents of up to tmem_estep_max_len() pairs
 bool tmem_estep_applicable(int K, int elem_size);
 int tmem_estep_max_len();
 int launch_estep_tmem(const EStepArgs& args, const DeviceDocs& docs, const int32_t* order, int64_t offset,

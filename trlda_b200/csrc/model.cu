@@ -206,7 +206,7 @@ struct trlda_model {
 	struct Bucket { int64_t offset, count; int n_max; };
 	std::vector<Bucket> buckets;
 	// documents longer than 192 / 160 / 128 / 64 pairs (prefix lengths of the length-sorted order): the cuts between
-	// the register-tile shapes of the resident E-step kernel
+	// the tile shapes of the tensor-memory E-step kernel
 	int64_t len_gt[4] = {0, 0, 0, 0};
 	bool force_generic = false;
 	// parked resident minibatches (trlda_upload_docs_slot / trlda_select_docs): the live buffers are swapped with a slot
@@ -231,7 +231,6 @@ struct trlda_model {
 	cudaEvent_t fork_event = nullptr, join_event[kAuxStreams] = {nullptr, nullptr, nullptr};
 	bool concurrent_buckets = true;
 	bool tmem_mode = true;       // TRLDA_ESTEP_TMEM=0: never use the tensor-memory-resident kernel (mixed mode)
-	bool resident_mode = true;   // TRLDA_ESTEP_RESIDENT=0: never use the register-resident kernel (mixed mode)
 	int stream_mode = 2;   // TRLDA_ESTEP_STREAM: 0 never use the streaming kernel, 1 only for warm-started E-steps, 2 always (default)
 	DevBuf ticks;    // debug phase timers of the fast E-step kernel (TRLDA_ESTEP_TICKS=1)
 	PinnedBuf staging, readback;
@@ -685,15 +684,11 @@ int run_estep(trlda_model* m, GammaSource src, const double* host_gamma, int max
 	a.max_iter = max_iter;
 	a.threshold = threshold;
 	a.ticks = m->ticks.as<unsigned long long>();
-	// Default path: the streaming kernel (estep_stream.cu).  Measured at cfg-3 it beats the cluster-resident kernel
-	// both for warm-started E-steps (one or two inner iterations: 2-3 sweeps) and for cold ones (the 126 MB L2
-	// serves the re-sweeps); the cluster kernels remain for shapes it does not cover (K too large for the per-lane
-	// register tile, unaligned K, very long documents)
 	const bool warm = src == GAMMA_KEEP;
-	// Mixed mode: the register-resident cluster kernel (estep_resident.cu).  The documents are sorted by length, longest
-	// first: [0, len_gt[0]) do not fit the register tile and go to the streaming kernel, the rest is cut by tile shape
+	// Mixed mode: the tensor-memory-resident cluster kernel (estep_tmem.cu).  The documents are sorted by length, longest
+	// first: [0, len_gt[0]) do not fit the on-chip tile and go to the streaming kernel, the rest is cut by tile shape
 	// (192 / 160 / 128 / 64 columns); a cut that would leave fewer than 64 documents joins the wider shape before it.
-	if(!m->force_generic && m->docs.B > 0 && m->resident_mode && resident_estep_applicable(m->K, m->beta_elem) &&
+	if(!m->force_generic && m->docs.B > 0 && m->tmem_mode && tmem_estep_applicable(m->K, m->beta_elem) &&
 	   (m->len_gt[0] == 0 || stream_estep_applicable(m->K, m->docs.n_max, m->beta_elem, m->smem_optin))) {
 		const int64_t B = m->docs.B;
 		const int64_t cut[5] = {m->len_gt[0], m->len_gt[1], m->len_gt[2], m->len_gt[3], B};
@@ -705,17 +700,11 @@ int run_estep(trlda_model* m, GammaSource src, const double* host_gamma, int max
 		}
 		struct Range { int64_t begin, end; int shape; };
 		Range pending{cut[0], cut[0], 0};
-		const bool tmem = m->tmem_mode && tmem_estep_applicable(m->K, m->beta_elem);
 		auto flush = [&]() {
 			if(pending.end > pending.begin && ok) {
 				Launch l(m, KK_ESTEP);
-				// tile in tensor memory (documents of up to 160 pairs), else in registers
-				if(tmem && pending.shape <= tmem_estep_max_len())
-					ok = launch_estep_tmem(a, m->docs, m->b_order.as<int32_t>(), pending.begin, pending.end - pending.begin,
-					                       pending.shape, m->stream) == 0;
-				else
-					ok = launch_estep_resident(a, m->docs, m->b_order.as<int32_t>(), pending.begin, pending.end - pending.begin,
-					                           pending.shape, m->stream) == 0;
+				ok = launch_estep_tmem(a, m->docs, m->b_order.as<int32_t>(), pending.begin, pending.end - pending.begin,
+				                       pending.shape, m->stream) == 0;
 			}
 		};
 		for(int i = 1; i < 5; ++i) {
@@ -723,7 +712,7 @@ int run_estep(trlda_model* m, GammaSource src, const double* host_gamma, int max
 				continue;
 			if(pending.end == pending.begin)
 				pending = {cut[i - 1], cut[i], cap[i]};
-			else if(cut[i] - cut[i - 1] < 64 && !(tmem && pending.shape > tmem_estep_max_len()))
+			else if(cut[i] - cut[i - 1] < 64)
 				pending.end = cut[i];                    // merged: the wider shape covers a few shorter documents
 			else {
 				flush();
@@ -734,10 +723,13 @@ int run_estep(trlda_model* m, GammaSource src, const double* host_gamma, int max
 		if(ok) {
 			m->gamma_valid = true;
 			m->stats.estep_docs = m->docs.B;
-			return check_launch(m, "estep_resident");
+			return check_launch(m, "estep_tmem");
 		}
-		return fail(m, TRLDA_ERR_CUDA, "The resident E-step kernel could not be launched.");
+		return fail(m, TRLDA_ERR_CUDA, "The tensor-memory E-step kernel could not be launched.");
 	}
+	// fp64 mode (and the shapes the TMEM kernel does not cover): the streaming kernel (estep_stream.cu), which re-reads
+	// the tile from L2 once per inner iteration; the shared-memory cluster kernels remain for what neither covers (K too
+	// large for the per-lane register tile, unaligned K, very long documents)
 	if(!m->force_generic && m->docs.B > 0 && (m->stream_mode == 2 || (m->stream_mode == 1 && warm)) &&
 	   stream_estep_applicable(m->K, m->docs.n_max, m->beta_elem, m->smem_optin)) {
 		{
@@ -1532,8 +1524,6 @@ int trlda_create(int kind, int num_words, int num_topics, int64_t num_documents,
 	configure_estep_fast(m->smem_optin);
 	if(const char* sm = getenv("TRLDA_ESTEP_STREAM"))
 		m->stream_mode = atoi(sm);
-	if(const char* rm = getenv("TRLDA_ESTEP_RESIDENT"))
-		m->resident_mode = atoi(rm) != 0;
 	if(const char* tm = getenv("TRLDA_ESTEP_TMEM"))
 		m->tmem_mode = atoi(tm) != 0;
 	if(const char* cb = getenv("TRLDA_CONCURRENT_BUCKETS"))
@@ -1578,10 +1568,10 @@ void trlda_destroy(trlda_model* m) {
 		                                     "pass1", "gamma/psi/delta", "pass2+push", "exchange+W", "results+doc_stat", "-"};
 		static const char* stream_names[10] = {"document setup", "sweep (stream columns)", "fold partial sums", "cluster exchange",
 		                                       "gamma/psi update + results", "convergence test", "-", "-", "-", "-"};
-		static const char* resident_names[8] = {"tile wait + registers + psi0", "pass B (acc) + butterfly", "gamma/psi update", "pass A (phi) + butterflies",
-		                                        "fold in smem + barrier + send", "exchange wait", "sum ranks + W", "results"};
-		if(m->resident_mode && m->beta_elem == 4 && resident_estep_applicable(m->K, m->beta_elem)) {
-			fprintf(stderr, "[trlda] resident E-step phase timers (one thread of rank 0, group 0 per cluster): %llu documents, %llu exchanges\n", t[15], t[14]);
+		static const char* resident_names[8] = {"tile -> TMEM + psi0", "pass B (acc) + butterfly", "gamma/psi update", "pass A (phi) + butterflies",
+		                                        "fold in smem + barrier + send", "exchange wait", "weights", "results"};
+		if(m->tmem_mode && m->beta_elem == 4 && tmem_estep_applicable(m->K, m->beta_elem)) {
+			fprintf(stderr, "[trlda] TMEM E-step phase timers (one thread of rank 0, group 0 per cluster): %llu documents, %llu exchanges\n", t[15], t[14]);
 			for(int i = 0; i < 8; ++i)
 				fprintf(stderr, "[trlda]   %-30s %10.0f cycles/doc %8.0f cycles/exchange\n", resident_names[i],
 				        t[15] ? (double) t[i] / (double) t[15] : 0.0, t[14] ? (double) t[i] / (double) t[14] : 0.0);
