@@ -1,36 +1,60 @@
-"""Where does the mixed-precision error come from?  Compares mixed vs fp64 on the GPU (fp64 matches the oracle to
-1e-11) for the smoke shape: gamma after one E-step at several iteration caps, then lambda after update_parameters."""
-import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np
-from trlda_b200 import capi
-from trlda_b200.synth import gamma_matrix, make_corpus
+"""Mixed-mode error of every golden case and of the smoke / oracle shapes under the candidate metrics:
+elementwise relative, column-wise infinity-norm relative (per document for gamma, per word for lambda), whole-array."""
+import os
+import sys
 
-K, V, B = 256, 2000, 96
-ptr, ids, cts = make_corpus(B, V, K, .1, .2, mean_length=80, seed=7)
-docs = capi.CSR(ptr, ids, cts)
-lam0, g0 = gamma_matrix(K, V, 8), gamma_matrix(K, B, 9)
-for max_iter in (0, 1, 2, 5, 10, 20, 50):
-    out = {}
-    for prec in ('fp64', 'mixed'):
-        m = capi.Model('online', V, K, 100000, .1, .2, precision=prec)
-        m.lambdas = lam0
-        g, s = m.update_variables(docs, g0, max_iter=max_iter)
-        out[prec] = (g, s, m.stats()['estep_doc_iterations'])
-    g64, s64, it64 = out['fp64']; g32, s32, it32 = out['mixed']
-    col = np.max(np.abs(g32 - g64), axis=0) / np.max(np.abs(g64), axis=0)
-    ew = np.abs(g32 - g64) / np.abs(g64)
-    sw = np.abs(s32 - s64) / np.maximum(np.abs(s64), 1e-12 * np.abs(s64).max())
-    print('max_iter %3d: gamma col-rel %.2e elementwise %.2e | sstats global %.2e elementwise %.2e | iters %d vs %d' % (
-        max_iter, col.max(), ew.max(), np.abs(s32 - s64).max() / np.abs(s64).max(), sw.max(), it64, it32))
-kw = dict(max_iter_tr=3, max_iter_inference=20, kappa=.7, tau=100.)
-lams = {}
-for prec in ('fp64', 'mixed'):
-    m = capi.Model('online', V, K, 100000, .1, .2, precision=prec)
-    m.lambdas = lam0
-    m.update_parameters(docs, gamma0=g0, **kw)
-    lams[prec] = m.lambdas
-e = np.abs(lams['mixed'] - lams['fp64']) / np.abs(lams['fp64'])
-i = np.unravel_index(np.argmax(e), e.shape)
-print('lambda elementwise max %.2e at %s value %.4e (lambda0 %.3e); 99.99%% quantile %.2e; global %.2e' % (
-    e.max(), i, lams['fp64'][i], lam0[i], np.quantile(e, .9999), np.abs(lams['mixed'] - lams['fp64']).max() / lams['fp64'].max()))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+import numpy as np
+from common import (load_case, rel_err, rel_err_columns, rel_err_elementwise, run_batch_case, run_cumulative_case,
+	run_online_case)
+from trlda_b200 import capi
+
+
+def report(tag, got, want):
+	got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+	if got.ndim < 2:
+		print('%-34s elementwise %.2e  vector inf-norm %.2e' % (tag, rel_err_elementwise(got, want), rel_err(got, want)))
+	else:
+		print('%-34s elementwise %.2e  column inf-norm %.2e  whole %.2e' % (
+			tag, rel_err_elementwise(got, want), rel_err_columns(got, want), rel_err(got, want)))
+
+
+for name in ('online_tr.npz', 'online_sgd.npz', 'online_adaptive.npz'):
+	case = load_case(name)
+	m = capi.Model('online', case['V'], case['K'], case['D'], case['alpha0'], case['eta0'], precision='mixed')
+	out = run_online_case(m, capi.CSR, case)
+	report(name + ' gamma', out['estep_gamma'], case['estep_gamma'])
+	report(name + ' lambda', out['lambda1'], case['lambda1'])
+	report(name + ' alpha', out['alpha1'], case['alpha1'])
+	print('%-34s eta %.2e' % (name, abs(out['eta1'] - float(case['eta1'])) / float(case['eta1'])))
+case = load_case('batch.npz')
+m = capi.Model('batch', case['V'], case['K'], 0, case['alpha0'], case['eta0'], precision='mixed')
+out = run_batch_case(m, capi.CSR, case)
+report('batch lambda', out['lambda1'], case['lambda1'])
+report('batch alpha', out['alpha1'], case['alpha1'])
+print('%-34s eta %.2e' % ('batch', abs(out['eta1'] - float(case['eta1'])) / float(case['eta1'])))
+case = load_case('cumulative.npz')
+m = capi.Model('cumulative', case['V'], case['K'], 0, case['alpha0'], case['eta0'], precision='mixed')
+out = run_cumulative_case(m, capi.CSR, case)
+for call in range(2):
+	report('cumulative lambda %d' % call, out['lambda1_%d' % call], case['lambda1_%d' % call])
+	report('cumulative alpha %d' % call, out['alpha1_%d' % call], case['alpha1_%d' % call])
+
+# the smoke shape and the two oracle shapes of test_online_update_parameters_vs_oracle
+from oracle import pyoracle
+from trlda_b200.synth import gamma_matrix, make_corpus
+for K, V, B, T, ml, seeds in ((256, 2000, 96, 3, 80, (7, 8, 9)), (100, 7000, 200, 10, 150, (1001, 2001, 3001)), (1000, 2000, 64, 10, 150, (1001, 2001, 3001))):
+	ptr, ids, cts = make_corpus(B, V, K, .1, .2, mean_length=ml, seed=seeds[0])
+	lam0, g0 = gamma_matrix(K, V, seeds[1]), gamma_matrix(K, B, seeds[2])
+	kwargs = dict(max_iter_tr=T, max_iter_inference=20, kappa=.7, tau=100., update_alpha=1, update_eta=1)
+	port = pyoracle.PortModel('online', V, K, 100000, .1, .2)
+	port.lambdas = lam0
+	port.update_parameters(pyoracle.CSR(ptr, ids, cts), gamma0=g0, **kwargs)
+	m = capi.Model('online', V, K, 100000, .1, .2, precision='mixed')
+	m.lambdas = lam0
+	m.update_parameters(capi.CSR(ptr, ids, cts), gamma0=g0, **kwargs)
+	report('online K=%d V=%d B=%d lambda' % (K, V, B), m.lambdas, port.lambdas)
+	report('online K=%d V=%d B=%d alpha' % (K, V, B), m.alpha, port.alpha)
+	print('%-34s eta %.2e' % ('', abs(m.eta - port.eta) / port.eta))

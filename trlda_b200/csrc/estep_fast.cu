@@ -300,7 +300,8 @@ k_estep_fast(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, in
 			for(int src = 0; src < C; ++src)
 				phi += (double) reinterpret_cast<const T*>(rows + (size_t) src * row_bytes)[j];
 			phi += 1e-100;
-			W[j] = (T) ((double) cnt[j] / phi);
+			// a weight beyond the float32 range (phi underflowed) would turn 0 * inf into NaN in the float32 products
+			W[j] = (T) (sizeof(T) == 4 ? fmin((double) cnt[j] / phi, 1e30) : (double) cnt[j] / phi);
 		}
 		__syncthreads();
 		return delta;

@@ -315,7 +315,8 @@ k_estep_stream(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, 
 				#pragma unroll
 				for(int o = 16; o > 0; o >>= 1)
 					phi += __shfl_xor_sync(0xffffffffu, phi, o);
-				wt = (T) __fdividef((float) cnt[j], fmaxf(phi, 1e-37f));     // lda.cpp:183,192,199 (+1e-100 only matters at 0)
+				// lda.cpp:183,192,199; the +1e-100 only matters at 0, where the weight must stay finite in float32
+				wt = (T) fminf(__fdividef((float) cnt[j], fmaxf(phi, 1e-37f)), 1e30f);
 			} else {
 				double part = 0.0;
 				#pragma unroll

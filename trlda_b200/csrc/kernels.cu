@@ -360,7 +360,9 @@ k_estep(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, int64_t
 				double* Wd = CLUSTERED ? cluster.map_shared_rank(W, dst) : W;
 				float* Wf = CLUSTERED ? cluster.map_shared_rank(W32, dst) : W32;
 				Wd[j] = wv;
-				Wf[j] = (float) wv;
+				// float32 products: a weight that overflowed float32 (phi underflowed, lda.cpp:183's 1e-100 floor) would turn
+				// 0 * inf into NaN where the fp64 reference gets 0
+				Wf[j] = (float) fmin(wv, 1e30);
 			}
 		}
 		if(CLUSTERED) cluster.sync(); else __syncthreads();

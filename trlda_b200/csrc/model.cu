@@ -271,6 +271,9 @@ struct trlda_model {
 	trlda_stats stats{};
 
 	std::string error;
+	// the reference held the GIL through every call; the binding releases it around the long ones, so calls on one
+	// model from several host threads are serialised here
+	std::recursive_mutex mu;
 
 	double* lambda() { return lam[cur].as<double>(); }
 	double* lambda_next() { return lam[1 - cur].as<double>(); }
@@ -460,8 +463,12 @@ int upload_docs(trlda_model* m, const trlda_docs* docs) {
 	const int64_t B = docs->num_docs;
 	const int64_t N = B ? docs->doc_ptr[B] : 0;
 	const int V = m->V;
-	if(N > INT32_MAX)
+	if(B && docs->doc_ptr[0] != 0)
+		return fail(m, TRLDA_ERR_ARG, "Document offsets must start at zero.");
+	if(N < 0 || N > INT32_MAX)
 		return fail(m, TRLDA_ERR_ARG, "Too many (word, count) pairs in one minibatch.");
+	if(N > 0 && (!docs->word_ids || !docs->counts))
+		return fail(m, TRLDA_ERR_ARG, "Documents must be given in CSR form.");
 
 	const bool host_timing = getenv("TRLDA_HOST_TIMING") != nullptr;
 	auto clock_now = [] { return std::chrono::steady_clock::now(); };
@@ -530,7 +537,7 @@ int upload_docs(trlda_model* m, const trlda_docs* docs) {
 			int oob = 0;
 			for(int64_t i = c0; i < c1; ++i) {
 				csum += cts[i];
-				oob |= (ids[i] < 0) | (ids[i] >= V);
+				oob |= (ids[i] < 0) | (ids[i] >= V) | ((cts[i] < 0) << 1);
 			}
 			counts_sum[t] = csum;
 			bad[t] = oob;
@@ -543,6 +550,8 @@ int upload_docs(trlda_model* m, const trlda_docs* docs) {
 			th.join();
 		for(int t = 0; t < T; ++t) {
 			total_count += counts_sum[t];
+			if(bad[t] & 2)
+				return fail(m, TRLDA_ERR_ARG, "Word counts should not be negative.");
 			if(bad[t])
 				return fail(m, TRLDA_ERR_ARG, "Word ID out of range.");
 		}
@@ -1621,6 +1630,7 @@ int trlda_kind(const trlda_model* m) { return m->kind; }
 int trlda_precision(const trlda_model* m) { return m->precision; }
 
 int trlda_set_precision(trlda_model* m, int precision) {
+	std::lock_guard<std::recursive_mutex> lock__(m->mu);
 	if(precision != TRLDA_PRECISION_FP64 && precision != TRLDA_PRECISION_MIXED)
 		return fail(m, TRLDA_ERR_ARG, "Unknown precision mode.");
 	if(precision != m->precision) {
@@ -1636,6 +1646,7 @@ int trlda_num_topics(const trlda_model* m) { return m->K; }
 int trlda_num_words(const trlda_model* m) { return m->V; }
 
 int trlda_get_lambda(trlda_model* m, double* out) {
+	std::lock_guard<std::recursive_mutex> lock__(m->mu);
 	TRY(set_device(m));
 	CUDA_TRY(m, cudaMemcpyAsync(out, m->lambda(), kv_bytes(m), cudaMemcpyDeviceToHost, m->stream));
 	CUDA_TRY(m, cudaStreamSynchronize(m->stream));
@@ -1644,6 +1655,7 @@ int trlda_get_lambda(trlda_model* m, double* out) {
 }
 
 int trlda_set_lambda(trlda_model* m, const double* lambda, int rows, int cols) {
+	std::lock_guard<std::recursive_mutex> lock__(m->mu);
 	if(rows != m->K || cols != m->V || !lambda)
 		return fail(m, TRLDA_ERR_ARG, "Lambda has wrong dimensionality.");      // lda.h:187
 	TRY(set_device(m));
@@ -1655,11 +1667,13 @@ int trlda_set_lambda(trlda_model* m, const double* lambda, int rows, int cols) {
 }
 
 int trlda_get_alpha(trlda_model* m, double* out) {
+	std::lock_guard<std::recursive_mutex> lock__(m->mu);
 	memcpy(out, m->alpha.data(), sizeof(double) * m->K);
 	return TRLDA_OK;
 }
 
 int trlda_set_alpha(trlda_model* m, const double* alpha, int n) {
+	std::lock_guard<std::recursive_mutex> lock__(m->mu);
 	if(n == 1 && m->K != 1) {                                                  // setAlpha(double), lda.h:146-150
 		if(alpha[0] < 0.)
 			return fail(m, TRLDA_ERR_ARG, "Alpha should not be negative.");
@@ -1677,11 +1691,13 @@ int trlda_set_alpha(trlda_model* m, const double* alpha, int n) {
 }
 
 int trlda_get_eta(trlda_model* m, double* eta) {
+	std::lock_guard<std::recursive_mutex> lock__(m->mu);
 	*eta = m->eta;
 	return TRLDA_OK;
 }
 
 int trlda_set_eta(trlda_model* m, double eta) {
+	std::lock_guard<std::recursive_mutex> lock__(m->mu);
 	if(eta < 0.)
 		return fail(m, TRLDA_ERR_ARG, "Eta should not be negative.");          // lda.h:173
 	m->eta = eta;
@@ -1689,11 +1705,13 @@ int trlda_set_eta(trlda_model* m, double eta) {
 }
 
 int trlda_get_num_documents(trlda_model* m, int64_t* n) {
+	std::lock_guard<std::recursive_mutex> lock__(m->mu);
 	*n = m->num_documents;
 	return TRLDA_OK;
 }
 
 int trlda_set_num_documents(trlda_model* m, int64_t n) {
+	std::lock_guard<std::recursive_mutex> lock__(m->mu);
 	if(n < 0)
 		return fail(m, TRLDA_ERR_ARG, "The number of documents should not be negative.");   // onlinelda.h:58
 	m->num_documents = n;
@@ -1701,11 +1719,13 @@ int trlda_set_num_documents(trlda_model* m, int64_t n) {
 }
 
 int trlda_get_update_count(trlda_model* m, int64_t* n) {
+	std::lock_guard<std::recursive_mutex> lock__(m->mu);
 	*n = m->update_count;
 	return TRLDA_OK;
 }
 
 int trlda_set_update_count(trlda_model* m, int64_t n) {
+	std::lock_guard<std::recursive_mutex> lock__(m->mu);
 	if(n < 0)
 		return fail(m, TRLDA_ERR_ARG, "The update count should not be negative.");          // onlinelda.h:72
 	m->update_count = n;
@@ -1713,12 +1733,14 @@ int trlda_set_update_count(trlda_model* m, int64_t n) {
 }
 
 int trlda_upload_docs(trlda_model* m, const trlda_docs* docs) {
+	std::lock_guard<std::recursive_mutex> lock__(m->mu);
 	m->live_slot = -1;
 	return upload_docs(m, docs);
 }
 
 
 int trlda_upload_docs_slot(trlda_model* m, const trlda_docs* docs, int slot) {
+	std::lock_guard<std::recursive_mutex> lock__(m->mu);
 	if(slot < 0 || slot >= 64)
 		return fail(m, TRLDA_ERR_ARG, "Minibatch slot out of range.");
 	if((int) m->slots.size() <= slot)
@@ -1739,6 +1761,7 @@ int trlda_upload_docs_slot(trlda_model* m, const trlda_docs* docs, int slot) {
 }
 
 int trlda_select_docs(trlda_model* m, int slot) {
+	std::lock_guard<std::recursive_mutex> lock__(m->mu);
 	if(slot < 0 || slot >= (int) m->slots.size() || !m->slots[slot].used)
 		return fail(m, TRLDA_ERR_ARG, "No minibatch has been uploaded into this slot.");
 	if(m->live_slot == slot)
@@ -1808,6 +1831,7 @@ static int gibbs_variables(trlda_model* m, const trlda_docs* docs, const double*
 
 int trlda_update_variables(trlda_model* m, const trlda_docs* docs, const double* latents, int latents_rows,
                            int64_t latents_cols, const trlda_params* params, double* gamma_out, double* sstats_out) {
+	std::lock_guard<std::recursive_mutex> lock__(m->mu);
 	if(params->inference_method == TRLDA_INFERENCE_GIBBS)
 		return gibbs_variables(m, docs, latents, latents_rows, latents_cols, params, gamma_out, sstats_out);
 	if(latents && (latents_rows != m->K || latents_cols != docs->num_docs))
@@ -1840,11 +1864,13 @@ int trlda_update_variables(trlda_model* m, const trlda_docs* docs, const double*
 }
 
 int trlda_update_parameters(trlda_model* m, const trlda_docs* docs, const trlda_params* params, double* result) {
+	std::lock_guard<std::recursive_mutex> lock__(m->mu);
 	TRY(upload_docs(m, docs));
 	return update_resident(m, params, result);
 }
 
 int trlda_update_parameters_resident(trlda_model* m, const trlda_params* params, double* result) {
+	std::lock_guard<std::recursive_mutex> lock__(m->mu);
 	if(!m->docs_resident)
 		return fail(m, TRLDA_ERR_ARG, "No minibatch resident on the device; call trlda_upload_docs first.");
 	TRY(set_device(m));
@@ -1854,6 +1880,7 @@ int trlda_update_parameters_resident(trlda_model* m, const trlda_params* params,
 int trlda_lower_bound(trlda_model* m, const trlda_docs* docs, const double* latents, int latents_rows,
                       int64_t latents_cols, const trlda_params* params, int64_t num_documents, double* bound_out,
                       double* per_doc_out) {
+	std::lock_guard<std::recursive_mutex> lock__(m->mu);
 	if(params->inference_method != TRLDA_INFERENCE_VI)
 		return fail(m, TRLDA_ERR_UNSUPPORTED, "Only variational inference ('VI') is implemented on the device.");
 	if(latents && (latents_rows != m->K || latents_cols != docs->num_docs))
@@ -1909,6 +1936,7 @@ int trlda_lower_bound(trlda_model* m, const trlda_docs* docs, const double* late
 }
 
 int trlda_inject_initial_gamma(trlda_model* m, const double* gamma0, int rows, int64_t cols) {
+	std::lock_guard<std::recursive_mutex> lock__(m->mu);
 	if(!gamma0 || rows != m->K || cols < 0)
 		return fail(m, TRLDA_ERR_ARG, "Initial gamma has wrong dimensionality.");
 	m->inj_gamma.assign(gamma0, gamma0 + (size_t) rows * cols);
@@ -1917,6 +1945,7 @@ int trlda_inject_initial_gamma(trlda_model* m, const double* gamma0, int rows, i
 }
 
 int trlda_inject_initial_lambda(trlda_model* m, const double* lambda, int rows, int cols) {
+	std::lock_guard<std::recursive_mutex> lock__(m->mu);
 	if(!lambda || rows != m->K || cols != m->V)
 		return fail(m, TRLDA_ERR_ARG, "Lambda has wrong dimensionality.");
 	m->inj_lambda.assign(lambda, lambda + (size_t) rows * cols);
@@ -1936,6 +1965,7 @@ int trlda_comm_unique_id(void* id_out) {
 }
 
 int trlda_comm_init(trlda_model* m, const void* id_bytes, int rank, int nranks) {
+	std::lock_guard<std::recursive_mutex> lock__(m->mu);
 	if(nranks < 1 || rank < 0 || rank >= nranks)
 		return fail(m, TRLDA_ERR_ARG, "Invalid rank / world size.");
 	if(nranks == 1)
@@ -2015,17 +2045,20 @@ int trlda_comm_size(const trlda_model* m) { return m->nranks; }
 void* trlda_stream(trlda_model* m) { return m->stream; }
 
 int trlda_synchronize(trlda_model* m) {
+	std::lock_guard<std::recursive_mutex> lock__(m->mu);
 	TRY(set_device(m));
 	CUDA_TRY(m, cudaStreamSynchronize(m->stream));
 	return TRLDA_OK;
 }
 
 int trlda_set_profiling(trlda_model* m, int on) {
+	std::lock_guard<std::recursive_mutex> lock__(m->mu);
 	m->profiling = on != 0;
 	return TRLDA_OK;
 }
 
 int trlda_get_stats(trlda_model* m, trlda_stats* out) {
+	std::lock_guard<std::recursive_mutex> lock__(m->mu);
 	TRY(set_device(m));
 	CUDA_TRY(m, cudaStreamSynchronize(m->stream));
 	collect_spans(m);
@@ -2044,6 +2077,7 @@ int trlda_get_stats(trlda_model* m, trlda_stats* out) {
 }
 
 int trlda_reset_stats(trlda_model* m) {
+	std::lock_guard<std::recursive_mutex> lock__(m->mu);
 	TRY(set_device(m));
 	CUDA_TRY(m, cudaStreamSynchronize(m->stream));
 	collect_spans(m);
@@ -2052,6 +2086,7 @@ int trlda_reset_stats(trlda_model* m) {
 }
 
 int trlda_get_row_sums(trlda_model* m, double* out) {
+	std::lock_guard<std::recursive_mutex> lock__(m->mu);
 	TRY(set_device(m));
 	TRY(ensure_small(m));
 	TRY(compute_rows(m, m->lambda(), m->rows_stat.as<double>()));

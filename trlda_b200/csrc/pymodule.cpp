@@ -105,6 +105,10 @@ int docs_converter(PyObject* obj, void* out_) {
 			} else if(!PyArg_ParseTuple(pair, "ll", &w, &c)) {                                // ldainterface.cpp:178
 				return 0;
 			}
+			if(w < INT32_MIN || w > INT32_MAX || c < INT32_MIN || c > INT32_MAX) {
+				PyErr_SetString(PyExc_OverflowError, "Word IDs and counts must fit 32-bit integers.");
+				return 0;
+			}
 			out.word_ids[t] = (int32_t) w;
 			out.counts[t] = (int32_t) c;
 		}
