@@ -96,6 +96,9 @@ typedef struct trlda_stats {
 	int64_t total_launches;                     /* all kernels launched since the last reset                */
 	int64_t h2d_bytes;                          /* host->device bytes since the last reset                  */
 	int64_t d2h_bytes;                          /* device->host bytes since the last reset                  */
+	int64_t estep_sweeps;                       /* sum over all E-steps since the last reset of (inner iterations + 1)
+	                                               per document: how often the E-step kernels went over a tile  */
+	int64_t estep_calls;                        /* E-steps (updateVariablesVI calls) since the last reset     */
 } trlda_stats;
 TRLDA_API const char* trlda_kernel_kind_name(int kind);
 
@@ -190,6 +193,13 @@ TRLDA_API int trlda_set_profiling(trlda_model* m, int on);    /* bracket every k
 TRLDA_API int trlda_get_stats(trlda_model* m, trlda_stats* out);
 TRLDA_API int trlda_reset_stats(trlda_model* m);
 TRLDA_API int trlda_get_row_sums(trlda_model* m, double* row_sums_K);   /* sum_w lambda_kw, a cheap per-step result */
+
+/* LDA::sample (lda.cpp:88-115): num_documents documents of Poisson(length) words drawn from the model's generative
+ * process (beta_k ~ Dirichlet(lambda_k), theta ~ Dirichlet(alpha)) on the device.  collapse = 0: every word is emitted
+ * as (word id, 1) in the order drawn, repeated ids included, like the reference; collapse = 1: unique (word id, count)
+ * pairs sorted by id, the form load_documents produces.  `out` receives a CSR view of host memory owned by the model,
+ * valid until the next trlda_sample / trlda_destroy on it.  Seeded by trlda_seed. */
+TRLDA_API int trlda_sample(trlda_model* m, int64_t num_documents, double length, int collapse, trlda_docs* out);
 
 /* device special functions evaluated on n host values (test hook pinning the in-kernel psi / psi' / lgamma
  * against python/tests/utils_test.py:33-51): which = 0 digamma fp64, 1 trigamma fp64, 2 lgamma fp64,

@@ -23,10 +23,11 @@ def models():
 @pytest.fixture(autouse=True)
 def _fixed_seeds():
 	"""the reference's directional tests (empirical Bayes, lower bound) draw their corpora with `sample()`; unseeded they
-	fail once in a while by chance, which says nothing about the code under test"""
+	fail once in a while by chance, which says nothing about the code under test (e.g. alpha = [.2, .01] yields no document
+	of the second topic among 100 with probability 1.4 %, and alpha[0] is then not identifiable: scripts/diag_eb.py)"""
 	import trlda
-	np.random.seed(20261017)
-	trlda.seed(20261017)
+	np.random.seed(1)
+	trlda.seed(1)
 	yield
 
 
@@ -211,17 +212,16 @@ def test_private_parity_seams_and_csr_input(models, oracle_built):
 
 def test_seed_makes_runs_reproducible(models):
 	import trlda
-	docs = None
-	results = []
+	docs = models.OnlineLDA(num_words=60, num_topics=8, num_documents=100).sample(20, 15)
+	results, corpora = [], []
 	for _ in range(2):
-		trlda.seed(42)
+		trlda.seed(42)        # same seed, same sequence of calls: same lambda0, same initial gamma, same sampled corpus
 		model = models.OnlineLDA(num_words=60, num_topics=8, num_documents=100)
-		if docs is None:
-			np.random.seed(1)
-			docs = model.sample(20, 15)
 		model.update_parameters(docs, max_iter_tr=2)
 		results.append(model.lambdas)
+		corpora.append(model.sample(5, 10))
 	assert np.array_equal(results[0], results[1])
+	assert corpora[0] == corpora[1]
 
 
 def test_mixed_precision_constructor_keyword(models):

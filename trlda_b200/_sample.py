@@ -1,32 +1,8 @@
 """
-Host-side samplers that sit beside the hot path in the reference (code/trlda/src/lda.cpp:88-115,
-utils.cpp:235-287, 294-330).  They are utilities for tests and examples, written with numpy; nothing here is
-timed or accelerated.
+Host-side helpers of trlda.utils that sit beside the hot path in the reference (utils.cpp:235-287, 294-330), written
+with numpy.  LDA::sample itself runs on the device (csrc/sample.cu, trlda_sample).
 """
 import numpy as np
-
-
-def sample_documents(lambdas, alpha, num_documents, length):
-	"""LDA::sample: beta_k ~ Dirichlet(lambda_k), theta ~ Dirichlet(alpha), Poisson(length) words per document,
-	every word emitted as (word_id, 1) — repeated ids are possible, exactly like the reference."""
-	lambdas = np.asarray(lambdas, dtype=np.float64)
-	alpha = np.asarray(alpha, dtype=np.float64).ravel()
-	K, V = lambdas.shape
-	beta = np.random.standard_gamma(np.maximum(lambdas, 1e-300))
-	beta = np.maximum(beta, 1e-300)
-	beta /= beta.sum(1, keepdims=True)
-	cdf = np.cumsum(beta, axis=1)
-	cdf /= cdf[:, -1:]
-	documents = []
-	for n in np.random.poisson(length, size=num_documents):
-		theta = np.random.standard_gamma(np.maximum(alpha, 1e-300))
-		theta = np.maximum(theta, 1e-300)
-		theta /= theta.sum()
-		topics = np.random.choice(K, size=n, p=theta)
-		u = np.random.rand(n)
-		words = [min(int(np.searchsorted(cdf[k], v, side='right')), V - 1) for k, v in zip(topics, u)]
-		documents.append([(w, 1) for w in words])
-	return documents
 
 
 def random_select(k, n):

@@ -64,7 +64,9 @@ class Stats(C.Structure):
 		('estep_docs', C.c_int64),
 		('total_launches', C.c_int64),
 		('h2d_bytes', C.c_int64),
-		('d2h_bytes', C.c_int64)]
+		('d2h_bytes', C.c_int64),
+		('estep_sweeps', C.c_int64),
+		('estep_calls', C.c_int64)]
 
 
 _P = C.POINTER
@@ -77,6 +79,7 @@ PROTOTYPES = {
 	'trlda_create': (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int64, _dbl, C.c_double, C.c_int, C.c_int, _P(C.c_void_p)]),
 	'trlda_destroy': (None, [C.c_void_p]),
 	'trlda_last_error': (C.c_char_p, [C.c_void_p]),
+	'trlda_sample': (C.c_int, [C.c_void_p, C.c_int64, C.c_double, C.c_int, _P(Docs)]),
 	'trlda_seed': (None, [C.c_uint64]),
 	'trlda_kind': (C.c_int, [C.c_void_p]),
 	'trlda_precision': (C.c_int, [C.c_void_p]),
@@ -379,7 +382,20 @@ class Model(object):
 			'estep_docs': int(s.estep_docs),
 			'total_launches': int(s.total_launches),
 			'h2d_bytes': int(s.h2d_bytes),
-			'd2h_bytes': int(s.d2h_bytes)}
+			'd2h_bytes': int(s.d2h_bytes),
+			'estep_sweeps': int(s.estep_sweeps),
+			'estep_calls': int(s.estep_calls)}
+
+	def sample(self, num_documents, length, collapse=False):
+		"""LDA::sample on the device; returns a CSR (collapse: unique (word, count) pairs sorted by word id)"""
+		view = Docs()
+		self._check(self._lib.trlda_sample(self.h, int(num_documents), float(length), int(bool(collapse)), C.byref(view)))
+		B = int(view.num_docs)
+		ptr = np.ctypeslib.as_array(view.doc_ptr, shape=(B + 1,)).copy()
+		N = int(ptr[-1])
+		ids = np.ctypeslib.as_array(view.word_ids, shape=(N,)).copy() if N else np.zeros(0, dtype=np.int32)
+		cts = np.ctypeslib.as_array(view.counts, shape=(N,)).copy() if N else np.zeros(0, dtype=np.int32)
+		return CSR(ptr, ids, cts)
 
 	def row_sums(self):
 		out = np.empty(self.K)

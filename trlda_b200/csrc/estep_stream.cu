@@ -495,6 +495,8 @@ k_estep_stream(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, 
 	++docs_done;
 	if(rank == 0 && tid == 0 && a.iterations)
 		a.iterations[d] = it;
+	if(rank == 0 && tid == 0 && a.sweeps)
+		atomicAdd(a.sweeps, (unsigned long long) (it + 1));
 	}
 	if(timing && rank == 0) {
 		for(int i = 0; i < 6; ++i)
@@ -524,7 +526,11 @@ template <typename T, int NW, int NVEC, int C, bool BULK, int DEPTH>
 static void launch_stream_b(const EStepArgs& args, const DeviceDocs& docs, const int32_t* order, int64_t offset,
                             int64_t count, int n_cap, size_t smem, cudaStream_t s) {
 	auto kernel = k_estep_stream<T, NW, NVEC, C, BULK, DEPTH>;
-	cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+	static size_t configured = 0;      // per instantiation: the attribute is set once (and again only if the tile grows)
+	if(smem > configured) {
+		cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+		configured = smem;
+	}
 	cudaLaunchConfig_t cfg = {};
 	cfg.gridDim = dim3((unsigned) (stream_grid_docs(count) * C));
 	cfg.blockDim = dim3(NW * 32);

@@ -573,6 +573,8 @@ k_estep_tmem(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, in
 					a.weight[begin + tg + c * GT] = (double) Wmine[c];
 			if(tg == 0 && a.iterations)
 				a.iterations[d] = it;
+			if(tg == 0 && a.sweeps)
+				atomicAdd(a.sweeps, (unsigned long long) (it + 1));
 		}
 		TRLDA_TTICK(7)
 		if(timing) {

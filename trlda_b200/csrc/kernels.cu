@@ -9,6 +9,7 @@
 // Reference citations are relative to /root/reference/code/trlda/src/.
 #include "kernels.cuh"
 #include "special.cuh"
+#include "rng.cuh"
 
 #include <cooperative_groups.h>
 #include <math_constants.h>
@@ -18,6 +19,17 @@
 namespace cg = cooperative_groups;
 
 namespace trlda {
+
+// SM count of the current device (one process drives one GPU): grids are sized in multiples of it
+static int sm_count() {
+	static const int n = [] {
+		int device = 0, count = 148;
+		if(cudaGetDevice(&device) != cudaSuccess || cudaDeviceGetAttribute(&count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || count < 1)
+			count = 148;
+		return count;
+	}();
+	return n;
+}
 
 static inline int ceil_div(int64_t a, int64_t b) { return (int) ((a + b - 1) / b); }
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
@@ -152,7 +164,7 @@ static inline int block_for_k(int K) { return std::min(256, std::max(32, round_u
 void launch_beta_prep(const double* lambda, const double* psi_rows, int K, int V, void* beta, int elem_size,
                       double* psi_partials, cudaStream_t s) {
 	const int block = block_for_k(K);
-	const int grid = std::min(V, 148 * 16);
+	const int grid = std::min(V, sm_count() * 16);
 	if(elem_size == 8)
 		k_beta_prep<double><<<grid, block, 0, s>>>(lambda, psi_rows, K, V, static_cast<double*>(beta), psi_partials);
 	else
@@ -802,7 +814,7 @@ __global__ void __launch_bounds__(NT, (NT == 128 && NCH <= 2 ? 5 : 1)) k_scatter
 
 template <typename TE, typename TB>
 static void launch_scatter_t(const ScatterArgs& a, const DeviceDocs& docs, cudaStream_t s) {
-	const int grid = std::min(a.V, 148 * 64);
+	const int grid = std::min(a.V, sm_count() * 64);
 	const int kpt = ceil_div(a.K, SCATTER_THREADS);
 	if(kpt <= 1) k_scatter<TE, TB, 1><<<grid, SCATTER_THREADS, 0, s>>>(a, docs);
 	else if(kpt <= 2) k_scatter<TE, TB, 2><<<grid, SCATTER_THREADS, 0, s>>>(a, docs);
@@ -814,7 +826,7 @@ static void launch_scatter_t(const ScatterArgs& a, const DeviceDocs& docs, cudaS
 
 void launch_scatter(const ScatterArgs& a, const DeviceDocs& docs, cudaStream_t s) {
 	if(a.etheta_elem == 4 && a.beta_elem == 4 && a.K % 4 == 0 && a.K <= 4096) {
-		const int grid = std::min(a.V, 148 * 64);
+		const int grid = std::min(a.V, sm_count() * 64);
 		const int chunks = a.K / 4;
 		if(chunks <= 128) k_scatter_vec<128, 1, 4><<<grid, 128, 0, s>>>(a, docs);
 		else if(chunks <= 256) k_scatter_vec<128, 2, 4><<<grid, 128, 0, s>>>(a, docs);
@@ -861,7 +873,7 @@ __global__ void __launch_bounds__(256) k_mstep(MStepArgs a) {
 
 void launch_mstep(const MStepArgs& a, cudaStream_t s) {
 	const int block = block_for_k(a.K);
-	const int grid = std::min(a.V, 148 * 16);
+	const int grid = std::min(a.V, sm_count() * 16);
 	if(a.beta_elem == 8) k_mstep<double><<<grid, block, 0, s>>>(a);
 	else k_mstep<float><<<grid, block, 0, s>>>(a);
 }
@@ -973,7 +985,7 @@ void launch_mstep_shard(const ShardMStepArgs& a, cudaStream_t s) {
 	if(words <= 0)
 		return;
 	const int block = std::min(256, std::max(32, round_up(a.K / 4, 32)));
-	const int grid = std::min(words, 148 * 8);
+	const int grid = std::min(words, sm_count() * 8);
 	if(a.beta_elem == 8 && a.sstats_elem == 8) k_mstep_shard<double, double><<<grid, block, 0, s>>>(a);
 	else if(a.beta_elem == 4 && a.sstats_elem == 4) k_mstep_shard<float, float><<<grid, block, 0, s>>>(a);
 	else if(a.beta_elem == 4) k_mstep_shard<float, double><<<grid, block, 0, s>>>(a);
@@ -1017,7 +1029,7 @@ void launch_init_update(const DeviceDocs& docs, int K, int V, double rho, double
                         const double* lambda_prime, double* lambda, const double* psi_rows, void* beta,
                         int beta_elem, const double* wordcount, cudaStream_t s) {
 	const int block = block_for_k(K);
-	const int grid = std::min(V, 148 * 16);
+	const int grid = std::min(V, sm_count() * 16);
 	if(beta_elem == 8)
 		k_init_update<double><<<grid, block, 0, s>>>(K, V, rho, eta, scale_k, lambda_prime, lambda, psi_rows,
 		                                              static_cast<double*>(beta), wordcount);
@@ -1068,7 +1080,7 @@ __global__ void __launch_bounds__(256) k_alpha_stats(const double* __restrict__ 
 void launch_alpha_stats(const double* gamma, int K, int64_t B, double* stat, cudaStream_t s) {
 	if(B == 0)
 		return;
-	k_alpha_stats<<<(unsigned) std::min<int64_t>(B, 148 * 16), block_for_k(K), 0, s>>>(gamma, K, B, stat);
+	k_alpha_stats<<<(unsigned) std::min<int64_t>(B, sm_count() * 16), block_for_k(K), 0, s>>>(gamma, K, B, stat);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1076,18 +1088,6 @@ void launch_alpha_stats(const double* gamma, int K, int64_t B, double* stat, cud
 // Counter-based (Philox4x32-10 keyed by seed, counter = element index and draw number), Marsaglia–Tsang
 // rejection with Box–Muller normals: the value of element i depends only on (seed, stream, i).
 // ------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void philox4x32(uint32_t c[4], uint32_t k0, uint32_t k1) {
-	#pragma unroll
-	for(int r = 0; r < 10; ++r) {
-		const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
-		const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
-		const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
-		c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
-		k0 += 0x9E3779B9u;
-		k1 += 0xBB67AE85u;
-	}
-}
-
 __global__ void __launch_bounds__(256) k_gamma_rng(double* __restrict__ out, int64_t n, uint64_t seed, uint64_t stream_id) {
 	const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
 	if(i >= n)
@@ -1285,7 +1285,7 @@ void launch_gibbs(const DeviceDocs& docs, int K, const void* beta, int beta_elem
 		return;
 	const int warps = 4;
 	const size_t smem = (size_t) warps * K * sizeof(double);
-	const unsigned grid = (unsigned) std::min<int64_t>((docs.B + warps - 1) / warps, 148 * 8);
+	const unsigned grid = (unsigned) std::min<int64_t>((docs.B + warps - 1) / warps, sm_count() * 8);
 	if(beta_elem == 4) {
 		cudaFuncSetAttribute(k_gibbs<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
 		k_gibbs<float><<<grid, warps * 32, smem, s>>>(docs, K, static_cast<const float*>(beta), alpha, theta0, occ_ptr, topics,
@@ -1421,7 +1421,7 @@ void launch_elbo_docs(const DeviceDocs& docs, int K, const double* lambda, const
                       const double* alpha, double alpha_const, const double* gamma, double* per_doc, cudaStream_t s) {
 	if(docs.B == 0)
 		return;
-	k_elbo_docs<<<(unsigned) std::min<int64_t>(docs.B, 148 * 8), block_for_k(K), (size_t) K * 8, s>>>(
+	k_elbo_docs<<<(unsigned) std::min<int64_t>(docs.B, sm_count() * 8), block_for_k(K), (size_t) K * 8, s>>>(
 		docs, K, lambda, psi_rows, alpha, alpha_const, gamma, per_doc);
 }
 
@@ -1442,7 +1442,7 @@ __global__ void __launch_bounds__(256) k_elbo_beta(const double* __restrict__ la
 
 void launch_elbo_beta(const double* lambda, const double* psi_rows, int K, int V, double eta, double* partial,
                       cudaStream_t s) {
-	k_elbo_beta<<<std::min(V, 148 * 16), block_for_k(K), 0, s>>>(lambda, psi_rows, K, V, eta, partial);
+	k_elbo_beta<<<std::min(V, sm_count() * 16), block_for_k(K), 0, s>>>(lambda, psi_rows, K, V, eta, partial);
 }
 
 // ------------------------------------------------------------------------------------------------------------

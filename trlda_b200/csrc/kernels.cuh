@@ -71,6 +71,7 @@ struct EStepArgs {
 	int32_t* iterations = nullptr;  // B out
 	int max_iter = 0;
 	double threshold = 0;
+	unsigned long long* sweeps = nullptr;  // optional counter: += inner iterations + 1 per document (tile sweeps)
 	unsigned long long* ticks = nullptr;   // optional phase timers (debug, TRLDA_ESTEP_TICKS=1): 16 sums of clock64 deltas
 };
 
@@ -116,6 +117,14 @@ int launch_estep_tmem(const EStepArgs& args, const DeviceDocs& docs, const int32
 void launch_gibbs(const DeviceDocs& docs, int K, const void* beta, int beta_elem, const double* alpha, const double* theta0,
                   const int64_t* occ_ptr, uint16_t* topics, int num_samples, int burn_in, uint64_t seed, double* theta_out,
                   double* sstats, cudaStream_t s);
+
+// LDA::sample on the device (sample.cu): row-wise CDFs of beta_k ~ Dirichlet(lambda_k), then one warp per document;
+// tokens / counts / lengths are B x cap, B x cap, B device arrays
+int sample_capacity(double length);
+size_t sample_smem_bytes(int K, int cap);
+void launch_sample_beta(const double* lambda, int K, int V, uint64_t seed, double* cdf, cudaStream_t s);
+int launch_sample_docs(const double* cdf, const double* alpha, int K, int V, int64_t B, double length, int cap, bool collapse,
+                       uint64_t seed, int32_t* tokens, int32_t* counts, int32_t* lengths, cudaStream_t s);
 
 constexpr int TRLDA_MAX_RANKS = 8;    // one NVSwitch node
 

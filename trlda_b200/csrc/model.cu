@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <nccl.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <algorithm>
 #include <chrono>
@@ -232,6 +233,11 @@ struct trlda_model {
 	bool concurrent_buckets = true;
 	bool tmem_mode = true;       // TRLDA_ESTEP_TMEM=0: never use the tensor-memory-resident kernel (mixed mode)
 	int stream_mode = 2;   // TRLDA_ESTEP_STREAM: 0 never use the streaming kernel, 1 only for warm-started E-steps, 2 always (default)
+	DevBuf sweeps;   // device counter behind trlda_stats.estep_sweeps
+	// trlda_sample: row-wise CDFs of beta ~ Dirichlet(lambda), padded token buffers, and the host copy handed to the caller
+	DevBuf sample_cdf, sample_tokens, sample_counts, sample_lengths;
+	std::vector<int64_t> sample_ptr;
+	std::vector<int32_t> sample_ids, sample_cts;
 	DevBuf ticks;    // debug phase timers of the fast E-step kernel (TRLDA_ESTEP_TICKS=1)
 	PinnedBuf staging, readback;
 	int64_t docs_total_count = 0;    // sum of all counts in the (global) minibatch
@@ -315,6 +321,7 @@ struct Launch {
 	int kind;
 	cudaEvent_t a = nullptr, b = nullptr;
 	Launch(trlda_model* m_, int kind_) : m(m_), kind(kind_) {
+		nvtxRangePushA(trlda_kernel_kind_name(kind));      // NVTX range per kernel kind (beta_prep, estep, scatter_mstep, ...)
 		m->stats.launches[kind]++;
 		m->stats.total_launches++;
 		if(m->profiling) {
@@ -324,6 +331,7 @@ struct Launch {
 		}
 	}
 	~Launch() {
+		nvtxRangePop();
 		if(m->profiling) {
 			cudaEventRecord(b, m->stream);
 			m->spans.push_back({kind, a, b});
@@ -693,6 +701,8 @@ int run_estep(trlda_model* m, GammaSource src, const double* host_gamma, int max
 	a.max_iter = max_iter;
 	a.threshold = threshold;
 	a.ticks = m->ticks.as<unsigned long long>();
+	a.sweeps = m->sweeps.as<unsigned long long>();
+	m->stats.estep_calls++;
 	const bool warm = src == GAMMA_KEEP;
 	// Mixed mode: the tensor-memory-resident cluster kernel (estep_tmem.cu).  The documents are sorted by length, longest
 	// first: [0, len_gt[0]) do not fit the on-chip tile and go to the streaming kernel, the rest is cut by tile shape
@@ -1546,6 +1556,8 @@ int trlda_create(int kind, int num_words, int num_topics, int64_t num_documents,
 	int status = TRLDA_OK;
 	auto init = [&]() -> int {
 		CUDA_TRY(m, m->lam[0].ensure(kv_bytes(m)));
+		CUDA_TRY(m, m->sweeps.ensure(sizeof(unsigned long long)));
+		CUDA_TRY(m, cudaMemset(m->sweeps.p, 0, sizeof(unsigned long long)));
 		TRY(ensure_small(m));
 		TRY(upload_alpha(m));
 		if(kind == TRLDA_KIND_CUMULATIVE) {
@@ -1603,7 +1615,8 @@ void trlda_destroy(trlda_model* m) {
 	DevBuf* bufs[] = {&m->ada_gradient, &m->lam[0], &m->lam[1], &m->beta, &m->sstats, &m->sstats32, &m->rows, &m->rows_prev, &m->rows_stat,
 	                  &m->psi_rows, &m->d_alpha, &m->partials, &m->vpartials, &m->scalars, &m->b_doc_ptr, &m->b_word_ids,
 	                  &m->b_counts, &m->b_word_ptr, &m->b_tok_doc, &m->b_tok_src, &m->b_order, &m->wordcount, &m->gamma, &m->etheta,
-	                  &m->etheta32, &m->weight, &m->doc_stat, &m->iterations, &m->gibbs_occ, &m->gibbs_topics};
+	                  &m->etheta32, &m->weight, &m->doc_stat, &m->iterations, &m->gibbs_occ, &m->gibbs_topics, &m->sweeps,
+	                  &m->sample_cdf, &m->sample_tokens, &m->sample_counts, &m->sample_lengths};
 	for(DevBuf* b : bufs)
 		b->release();
 	for(auto& slot : m->slots) {
@@ -1935,6 +1948,63 @@ int trlda_lower_bound(trlda_model* m, const trlda_docs* docs, const double* late
 	return TRLDA_OK;
 }
 
+int trlda_sample(trlda_model* m, int64_t num_documents, double length, int collapse, trlda_docs* out) {
+	std::lock_guard<std::recursive_mutex> lock__(m->mu);
+	TRY(set_device(m));
+	if(!out || num_documents < 0 || !(length >= 0.0) || length > 1e6)
+		return fail(m, TRLDA_ERR_ARG, "sample: num_documents should be non-negative and length in [0, 1e6].");
+	if(m->lambda_sharded)
+		return fail(m, TRLDA_ERR_UNSUPPORTED, "sample: lambda is sharded over ranks.");
+	const int64_t B = num_documents;
+	const int cap = sample_capacity(length);
+	if(sample_smem_bytes(m->K, cap) > (size_t) m->smem_optin)
+		return fail(m, TRLDA_ERR_UNSUPPORTED, "sample: too many topics / too long documents for the sampler's shared memory.");
+	const uint64_t seed = current_seed() ^ (next_stream_id() * 0x9E3779B97F4A7C15ull);
+	CUDA_TRY(m, m->sample_cdf.ensure(kv_bytes(m)));
+	CUDA_TRY(m, m->sample_tokens.ensure(sizeof(int32_t) * (size_t) std::max<int64_t>(B, 1) * cap));
+	CUDA_TRY(m, m->sample_counts.ensure(sizeof(int32_t) * (size_t) std::max<int64_t>(B, 1) * cap));
+	CUDA_TRY(m, m->sample_lengths.ensure(sizeof(int32_t) * (size_t) std::max<int64_t>(B, 1)));
+	TRY(upload_alpha(m));
+	{
+		Launch l(m, KK_RNG);
+		launch_sample_beta(m->lambda(), m->K, m->V, seed, m->sample_cdf.as<double>(), m->stream);
+	}
+	{
+		Launch l(m, KK_RNG);
+		if(launch_sample_docs(m->sample_cdf.as<double>(), m->d_alpha.as<double>(), m->K, m->V, B, length, cap, collapse != 0, seed,
+		                      m->sample_tokens.as<int32_t>(), m->sample_counts.as<int32_t>(), m->sample_lengths.as<int32_t>(), m->stream) != 0)
+			return fail(m, TRLDA_ERR_CUDA, "sample: the kernel could not be configured.");
+	}
+	TRY(check_launch(m, "sample"));
+	std::vector<int32_t> lengths((size_t) B), tokens((size_t) B * cap), counts(collapse ? (size_t) B * cap : 0);
+	if(B) {
+		CUDA_TRY(m, cudaMemcpyAsync(lengths.data(), m->sample_lengths.p, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, m->stream));
+		CUDA_TRY(m, cudaMemcpyAsync(tokens.data(), m->sample_tokens.p, sizeof(int32_t) * (size_t) B * cap, cudaMemcpyDeviceToHost, m->stream));
+		if(collapse)
+			CUDA_TRY(m, cudaMemcpyAsync(counts.data(), m->sample_counts.p, sizeof(int32_t) * (size_t) B * cap, cudaMemcpyDeviceToHost, m->stream));
+	}
+	CUDA_TRY(m, cudaStreamSynchronize(m->stream));
+	m->stats.d2h_bytes += sizeof(int32_t) * (size_t) B * cap * (collapse ? 2 : 1);
+	m->sample_ptr.assign((size_t) B + 1, 0);
+	for(int64_t d = 0; d < B; ++d)
+		m->sample_ptr[d + 1] = m->sample_ptr[d] + lengths[d];
+	const int64_t N = m->sample_ptr[B];
+	m->sample_ids.resize((size_t) N);
+	m->sample_cts.resize((size_t) N);
+	for(int64_t d = 0; d < B; ++d) {
+		const int64_t o = m->sample_ptr[d];
+		for(int j = 0; j < lengths[d]; ++j) {
+			m->sample_ids[o + j] = tokens[(size_t) d * cap + j];
+			m->sample_cts[o + j] = collapse ? counts[(size_t) d * cap + j] : 1;
+		}
+	}
+	out->num_docs = B;
+	out->doc_ptr = m->sample_ptr.data();
+	out->word_ids = m->sample_ids.data();
+	out->counts = m->sample_cts.data();
+	return TRLDA_OK;
+}
+
 int trlda_inject_initial_gamma(trlda_model* m, const double* gamma0, int rows, int64_t cols) {
 	std::lock_guard<std::recursive_mutex> lock__(m->mu);
 	if(!gamma0 || rows != m->K || cols < 0)
@@ -2072,6 +2142,11 @@ int trlda_get_stats(trlda_model* m, trlda_stats* out) {
 		m->stats.estep_doc_iterations = total;
 		m->stats.estep_docs = m->docs.B;
 	}
+	if(m->sweeps.p) {
+		unsigned long long total = 0;
+		CUDA_TRY(m, cudaMemcpy(&total, m->sweeps.p, sizeof(total), cudaMemcpyDeviceToHost));
+		m->stats.estep_sweeps = (int64_t) total;
+	}
 	*out = m->stats;
 	return TRLDA_OK;
 }
@@ -2082,6 +2157,8 @@ int trlda_reset_stats(trlda_model* m) {
 	CUDA_TRY(m, cudaStreamSynchronize(m->stream));
 	collect_spans(m);
 	m->stats = trlda_stats{};
+	if(m->sweeps.p)
+		CUDA_TRY(m, cudaMemset(m->sweeps.p, 0, sizeof(unsigned long long)));
 	return TRLDA_OK;
 }
 

@@ -384,25 +384,40 @@ int LDA_set_precision(LDAObject* self, PyObject* value, void*) {
 	return 0;
 }
 
-// sample(num_documents, length): host-side generative sampler (LDA::sample, lda.cpp:88-115) — not on the hot path;
-// delegated to the numpy helper trlda_b200._sample.sample_documents
+// sample(num_documents, length): LDA::sample (lda.cpp:88-115) on the device (trlda_sample); returns the reference's
+// list of lists of (word_id, 1) — or, with collapse=True, unique (word_id, count) pairs sorted by id
 PyObject* LDA_sample(LDAObject* self, PyObject* args, PyObject* kwds) {
 	REQUIRE_MODEL(self, nullptr);
-	const char* kwlist[] = {"num_documents", "length", nullptr};
+	const char* kwlist[] = {"num_documents", "length", "collapse", nullptr};
 	int num_documents;
 	double length;
-	if(!PyArg_ParseTupleAndKeywords(args, kwds, "id", const_cast<char**>(kwlist), &num_documents, &length))
+	int collapse = 0;
+	if(!PyArg_ParseTupleAndKeywords(args, kwds, "id|p", const_cast<char**>(kwlist), &num_documents, &length, &collapse))
 		return nullptr;
-	PyObject* module = PyImport_ImportModule("trlda_b200._sample");
-	if(!module)
+	trlda_docs view;
+	int status;
+	Py_BEGIN_ALLOW_THREADS
+	status = trlda_sample(self->m, num_documents, length, collapse, &view);
+	Py_END_ALLOW_THREADS
+	if(status != TRLDA_OK) {
+		PyErr_SetString(PyExc_RuntimeError, trlda_last_error(self->m));
 		return nullptr;
-	PyObject* lambdas = LDA_lambda(self, nullptr);
-	PyObject* alpha = lambdas ? LDA_alpha(self, nullptr) : nullptr;
-	PyObject* result = alpha ? PyObject_CallMethod(module, "sample_documents", "OOid", lambdas, alpha, num_documents, length) : nullptr;
-	Py_XDECREF(lambdas);
-	Py_XDECREF(alpha);
-	Py_DECREF(module);
-	return result;
+	}
+	PyObject* docs = PyList_New(view.num_docs);
+	if(!docs)
+		return nullptr;
+	for(int64_t d = 0; d < view.num_docs; ++d) {
+		const int64_t begin = view.doc_ptr[d], end = view.doc_ptr[d + 1];
+		PyObject* doc = PyList_New(end - begin);
+		if(!doc) {
+			Py_DECREF(docs);
+			return nullptr;
+		}
+		for(int64_t j = begin; j < end; ++j)
+			PyList_SET_ITEM(doc, j - begin, Py_BuildValue("(ii)", (int) view.word_ids[j], (int) view.counts[j]));
+		PyList_SET_ITEM(docs, d, doc);
+	}
+	return docs;
 }
 
 // update_variables / do_e_step (ldainterface.cpp:311-390)
@@ -777,7 +792,7 @@ PyGetSetDef LDA_getset[] = {
 	{nullptr, nullptr, nullptr, nullptr, nullptr}};
 
 PyMethodDef LDA_methods[] = {
-	{"sample", (PyCFunction) LDA_sample, METH_VARARGS | METH_KEYWORDS, "sample(num_documents, length)"},
+	{"sample", (PyCFunction) LDA_sample, METH_VARARGS | METH_KEYWORDS, "sample(num_documents, length, collapse=False)"},
 	{"update_variables", (PyCFunction) LDA_update_variables, METH_VARARGS | METH_KEYWORDS, update_variables_doc},
 	{"do_e_step", (PyCFunction) LDA_update_variables, METH_VARARGS | METH_KEYWORDS, update_variables_doc},   // module.cpp:99-106
 	{"lower_bound", (PyCFunction) LDA_lower_bound, METH_VARARGS | METH_KEYWORDS,

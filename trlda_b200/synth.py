@@ -10,15 +10,16 @@ form `load_documents` produces (python/utils/load_documents.py:41-44).
 import numpy as np
 
 
-def make_corpus(num_docs, num_words, num_topics, alpha=.1, eta=.2, mean_length=150, seed=0):
+def make_corpus(num_docs, num_words, num_topics, alpha=.1, eta=.2, mean_length=150, seed=0, doc_seed=None):
 	"""
 	Returns the minibatch in CSR form: (doc_ptr[int64, B+1], word_ids[int32, N], counts[int32, N]).
 
 	beta_k ~ Dirichlet(eta 1_V) is drawn as a normalised standard_gamma(eta, V) from a per-topic stream so
 	that the K x V matrix never has to be held (cfg-3: 800 MB); theta_d ~ Dirichlet(alpha 1_K);
-	length_d ~ Poisson(mean_length).
+	length_d ~ Poisson(mean_length).  `seed` fixes the corpus (its topics); `doc_seed` (default: seed) the documents
+	drawn from it, so that several processes can draw different documents of ONE corpus.
 	"""
-	rng = np.random.Generator(np.random.PCG64(seed))
+	rng = np.random.Generator(np.random.PCG64(seed if doc_seed is None else [seed, 7919, doc_seed]))
 	lengths = rng.poisson(mean_length, size=num_docs).astype(np.int64)
 	total = int(lengths.sum())
 	doc_of_token = np.repeat(np.arange(num_docs, dtype=np.int64), lengths)
