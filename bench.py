@@ -519,6 +519,50 @@ def e2e_python(run, w, precision, lam0, batches_np, steps):
 		'api': 'trlda.models.OnlineLDA.update_parameters(list of lists of (word_id, count))', 'precision': getattr(model, 'precision', precision)}
 
 
+def e2e_file(run, w, precision, lam0, batches_np, steps):
+	"""training straight from the reference's text format: the native reader (memory-mapped file, background parser,
+	pinned CSR batches `prefetch` ahead) feeding update_parameters; the Python loader of the reference's format is timed
+	on the same file for comparison (parsing only)"""
+	from trlda_b200 import capi
+	from trlda_b200.utils.load_documents import load_documents
+	use = batches_np[:steps + 1]
+	fd, path = tempfile.mkstemp(suffix='.txt')
+	os.close(fd)
+	try:
+		with open(path, 'w') as handle:
+			for ptr, ids, cts in use:
+				pairs = np.char.add(np.char.add(ids.astype(str), ':'), cts.astype(str))
+				for d in range(len(ptr) - 1):
+					handle.write(str(ptr[d + 1] - ptr[d]) + ' ' + ' '.join(pairs[ptr[d]:ptr[d + 1]]) + '\n')
+		size = os.path.getsize(path)
+		t0 = time.perf_counter()
+		parsed = sum(b.num_docs for b in capi.Reader(path, batch_size=w['B'], prefetch=2, copy=False))
+		native_s = time.perf_counter() - t0
+		t0 = time.perf_counter()
+		first = next(load_documents(path, batch_size=w['B']))
+		python_s = (time.perf_counter() - t0) * len(use)
+		model = capi.Model('online', w['V'], w['K'], w['D'], w['alpha'], w['eta'], device=run.local_rank, precision=precision)
+		model.lambdas = lam0
+		params = dict(w['params'])
+		reader = capi.Reader(path, batch_size=w['B'], prefetch=2, copy=False)
+		model.update_parameters(next(reader), **params)          # warm-up on the first batch
+		run.torch.cuda.synchronize()
+		t0 = time.perf_counter()
+		docs = 0
+		for batch in reader:
+			if batch.num_docs:
+				model.update_parameters(batch, **params)
+				docs += batch.num_docs
+		model.row_sums()
+		s = time.perf_counter() - t0
+		model.close()
+		return {'value': docs / s, 'unit': 'docs/s', 'ms_per_step': s * 1e3 / max(docs / w['B'], 1), 'file_bytes': size,
+			'what': 'text file -> trlda_reader (background parser, pinned CSR) -> trlda_update_parameters, wall clock',
+			'native_parse_docs_per_s': parsed / native_s, 'python_load_documents_docs_per_s': len(first) * len(use) / python_s}
+	finally:
+		os.unlink(path)
+
+
 def main():
 	args = parse_args()
 	w = dict(WORKLOADS[args.workload])
@@ -642,6 +686,10 @@ def main():
 			line['e2e_python'] = e2e_python(run, w, args.precision, lam0, docs_np, min(args.steps, 3))
 		except Exception as error:                # noqa: BLE001
 			line['e2e_python'] = {'error': str(error)[:200]}
+		try:
+			line['e2e_file'] = e2e_file(run, w, args.precision, lam0, docs_np, min(args.steps, 3))
+		except Exception as error:                # noqa: BLE001
+			line['e2e_file'] = {'error': str(error)[:200]}
 
 	if run.rank == 0 and world == 1 and not args.no_cpu_baseline:
 		cores = use_all_cores()

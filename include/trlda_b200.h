@@ -35,6 +35,7 @@ extern "C" {
 #define TRLDA_ERR_ARG       1   /* reference would have thrown TRLDA::Exception -> RuntimeError */
 #define TRLDA_ERR_CUDA      2   /* CUDA / NCCL failure, or no device                              */
 #define TRLDA_ERR_UNSUPPORTED 3 /* e.g. inference_method == GIBBS in update_parameters / lower_bound     */
+#define TRLDA_END           4   /* trlda_reader_next: no more batches                             */
 
 /* model kinds: the three concrete subclasses of TRLDA::LDA */
 #define TRLDA_KIND_ONLINE     0   /* code/trlda/include/onlinelda.h:7     */
@@ -200,6 +201,18 @@ TRLDA_API int trlda_get_row_sums(trlda_model* m, double* row_sums_K);   /* sum_w
  * pairs sorted by id, the form load_documents produces.  `out` receives a CSR view of host memory owned by the model,
  * valid until the next trlda_sample / trlda_destroy on it.  Seeded by trlda_seed. */
 TRLDA_API int trlda_sample(trlda_model* m, int64_t num_documents, double length, int collapse, trlda_docs* out);
+
+/* Native reader for the text format of python/utils/load_documents.py:6-69 (one document per line,
+ * `N id:cnt id:cnt ...`, first field ignored): the file is memory-mapped and parsed by a background thread into CSR
+ * minibatches of `batch_size` documents (0: the whole file) in pinned host memory, `prefetch` batches ahead of the
+ * consumer.  Batches come in the reference generator's order: full batches, then the remainder — yielded even if it
+ * is empty (load_documents.py:63) — then TRLDA_END.  The view handed out by trlda_reader_next stays valid until the
+ * call after the next one. */
+typedef struct trlda_reader trlda_reader;
+TRLDA_API int trlda_reader_open(const char* path, int64_t batch_size, int prefetch, trlda_reader** out);
+TRLDA_API int trlda_reader_next(trlda_reader* r, trlda_docs* out, int* pinned);
+TRLDA_API void trlda_reader_close(trlda_reader* r);
+TRLDA_API const char* trlda_reader_last_error(const trlda_reader* r);
 
 /* device special functions evaluated on n host values (test hook pinning the in-kernel psi / psi' / lgamma
  * against python/tests/utils_test.py:33-51): which = 0 digamma fp64, 1 trigamma fp64, 2 lgamma fp64,

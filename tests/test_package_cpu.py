@@ -73,7 +73,3 @@ def test_host_samplers():
 		random_select(10, 4)                                          # utils_test.py:29
 	x = sample_dirichlet(10, 7, .5)
 	assert x.shape == (10, 7) and np.allclose(x.sum(0), 1.)
-	from trlda_b200._sample import sample_documents
-	np.random.seed(3)
-	docs = sample_documents(np.random.gamma(100., .01, size=(4, 30)), np.full(4, .1), 6, 8)
-	assert len(docs) == 6 and all(c == 1 and 0 <= w < 30 for d in docs for w, c in d)

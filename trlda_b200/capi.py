@@ -116,6 +116,10 @@ PROTOTYPES = {
 	'trlda_get_row_sums': (C.c_int, [C.c_void_p, _dbl]),
 	'trlda_device_special': (C.c_int, [C.c_int, C.c_int, _dbl, C.c_int64, _dbl]),
 	'trlda_polygamma': (C.c_double, [C.c_int, C.c_double]),
+	'trlda_reader_open': (C.c_int, [C.c_char_p, C.c_int64, C.c_int, _P(C.c_void_p)]),
+	'trlda_reader_next': (C.c_int, [C.c_void_p, _P(Docs), _P(C.c_int)]),
+	'trlda_reader_close': (None, [C.c_void_p]),
+	'trlda_reader_last_error': (C.c_char_p, [C.c_void_p]),
 }
 
 _lib = None
@@ -401,6 +405,56 @@ class Model(object):
 		out = np.empty(self.K)
 		self._check(self._lib.trlda_get_row_sums(self.h, _dptr(out)))
 		return out
+
+
+class Reader(object):
+	"""Native reader of the reference's text format (`N id:cnt ...` per line): a background thread parses the memory-mapped
+	file into pinned CSR minibatches, `prefetch` batches ahead.  Iterating yields CSR objects in the order of the
+	reference's load_documents generator (the final remainder is yielded even when empty).  With copy=False the arrays
+	are views of the reader's ring buffers, valid until the batch after the next one is requested."""
+	END = 4
+
+	def __init__(self, path, batch_size=None, prefetch=2, copy=True):
+		self._lib = lib()
+		self.h = C.c_void_p()
+		self.copy = copy
+		status = self._lib.trlda_reader_open(os.fsencode(path), int(batch_size or 0), int(prefetch), C.byref(self.h))
+		if status != 0:
+			raise IOError(self._lib.trlda_reader_last_error(None).decode())
+		self.pinned = None
+
+	def close(self):
+		if self.h:
+			self._lib.trlda_reader_close(self.h)
+			self.h = C.c_void_p()
+
+	def __del__(self):
+		self.close()
+
+	def __iter__(self):
+		return self
+
+	def __next__(self):
+		if not self.h:
+			raise StopIteration
+		view, pinned = Docs(), C.c_int(0)
+		status = self._lib.trlda_reader_next(self.h, C.byref(view), C.byref(pinned))
+		if status == self.END:
+			self.close()
+			raise StopIteration
+		if status != 0:
+			message = self._lib.trlda_reader_last_error(self.h).decode()
+			self.close()
+			raise ValueError(message)
+		self.pinned = bool(pinned.value)
+		B = int(view.num_docs)
+		ptr = np.ctypeslib.as_array(view.doc_ptr, shape=(B + 1,))
+		N = int(ptr[-1])
+		ids = np.ctypeslib.as_array(view.word_ids, shape=(N,)) if N else np.zeros(0, dtype=np.int32)
+		cts = np.ctypeslib.as_array(view.counts, shape=(N,)) if N else np.zeros(0, dtype=np.int32)
+		if self.copy:
+			ptr, ids, cts = ptr.copy(), ids.copy(), cts.copy()
+		return CSR(ptr, ids, cts)
 
 
 def comm_unique_id():

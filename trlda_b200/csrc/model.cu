@@ -810,23 +810,22 @@ int reduce_doc_stat(trlda_model* m) {
 }
 
 // Builds the word-sorted token list (CSC view) of the resident minibatch from the pinned staging copy and sends it
-// to the device.  Stable counting sort, parallel over word ranges: thread t owns the words [V t / T, V (t+1) / T),
-// scans the whole token stream in order and places only its own words, so a word's tokens stay in document order
-// whatever the number of threads.
+// to the device.  Stable counting sort in O(N + T V): thread t owns a contiguous range of the token stream, counts its
+// words, the per-(word, thread) offsets follow from one pass over the T histograms, and every thread places its own
+// tokens — a word's tokens stay in document order whatever the number of threads.
 int ensure_csc(trlda_model* m) {
 	if(!m->csc_pending)
 		return TRLDA_OK;
 	m->csc_pending = false;
 	const int64_t B = m->docs.B, N = m->docs.N;
-	const int V = m->V, T = m->csc_threads;
+	const int V = m->V;
+	const int T = std::max(1, m->csc_threads);
 	char* base = m->staging.as<char>();
 	const int64_t* s_ptr = reinterpret_cast<const int64_t*>(base + m->stage_off[0]);
 	const int32_t* ids = reinterpret_cast<const int32_t*>(base + m->stage_off[1]);
 	int32_t* s_wptr = reinterpret_cast<int32_t*>(base + m->stage_off[2]);
 	int32_t* s_tdoc = reinterpret_cast<int32_t*>(base + m->stage_off[3]);
 	int32_t* s_tsrc = reinterpret_cast<int32_t*>(base + m->stage_off[4]);
-	memset(s_wptr, 0, sizeof(int32_t) * ((size_t) V + 1));
-	auto range_of = [&](int t) { return std::make_pair((int32_t) ((int64_t) V * t / T), (int32_t) ((int64_t) V * (t + 1) / T)); };
 	auto run = [&](auto&& fn) {
 		std::vector<std::thread> pool;
 		for(int t = 1; t < T; ++t)
@@ -835,27 +834,36 @@ int ensure_csc(trlda_model* m) {
 		for(auto& th : pool)
 			th.join();
 	};
+	// thread t takes the documents [d0(t), d0(t+1)), cut where the token stream passes t N / T
+	std::vector<int64_t> doc_cut(T + 1, B);
+	doc_cut[0] = 0;
+	for(int t = 1; t < T; ++t)
+		doc_cut[t] = std::lower_bound(s_ptr, s_ptr + B, N * t / T) - s_ptr;
+	std::vector<std::vector<int32_t>> hist(T);
 	run([&](int t) {
-		const auto r = range_of(t);
-		for(int64_t i = 0; i < N; ++i) {
-			const int32_t w = ids[i];
-			if(w >= r.first && w < r.second)
-				s_wptr[w + 1]++;
-		}
+		hist[t].assign((size_t) V, 0);
+		int32_t* h = hist[t].data();
+		for(int64_t i = s_ptr[doc_cut[t]]; i < s_ptr[doc_cut[t + 1]]; ++i)
+			h[ids[i]]++;
 	});
-	for(int w = 0; w < V; ++w)
-		s_wptr[w + 1] += s_wptr[w];
-	std::vector<int32_t> cursor(s_wptr, s_wptr + V);
+	// word_ptr and, in place of the counts, every thread's first slot of every word
+	int32_t total = 0;
+	for(int w = 0; w < V; ++w) {
+		s_wptr[w] = total;
+		for(int t = 0; t < T; ++t) {
+			const int32_t c = hist[t][w];
+			hist[t][w] = total;
+			total += c;
+		}
+	}
+	s_wptr[V] = total;
 	run([&](int t) {
-		const auto r = range_of(t);
-		for(int64_t d = 0; d < B; ++d)
+		int32_t* cursor = hist[t].data();
+		for(int64_t d = doc_cut[t]; d < doc_cut[t + 1]; ++d)
 			for(int64_t i = s_ptr[d]; i < s_ptr[d + 1]; ++i) {
-				const int32_t w = ids[i];
-				if(w >= r.first && w < r.second) {
-					const int32_t pos = cursor[w]++;
-					s_tdoc[pos] = (int32_t) d;
-					s_tsrc[pos] = (int32_t) i;
-				}
+				const int32_t pos = cursor[ids[i]]++;
+				s_tdoc[pos] = (int32_t) d;
+				s_tsrc[pos] = (int32_t) i;
 			}
 	});
 	if(N) {

@@ -6,7 +6,9 @@ other field is `word_id:count`.
 `load_documents` keeps the reference's behaviour exactly (list of lists of (id, count) tuples; with `batch_size`
 a generator of batches, fixed-size or Poisson-sized, the final partial batch always yielded).
 `load_documents_csr` yields the same batches already packed as (doc_ptr, word_ids, counts) numpy arrays, which
-the models accept directly and which skips the per-word Python objects.
+the models accept directly and which skips the per-word Python objects.  With a fixed batch size it is served by the
+native reader (csrc/ingest.cu): the file is memory-mapped and parsed by a background thread into pinned CSR batches a
+few batches ahead of the training loop; the pure-Python path remains for `stochastic=True` (numpy's Poisson stream).
 """
 import numpy as np
 from numpy.random import poisson
@@ -77,8 +79,16 @@ def _parse_arrays(line):
 	return flat[0::2].astype(np.int32), flat[1::2].astype(np.int32)
 
 
-def load_documents_csr(filepath, batch_size=None, stochastic=False):
+def load_documents_csr(filepath, batch_size=None, stochastic=False, native=True, prefetch=2):
 	"""Same batching as L{load_documents}, but every batch is a (doc_ptr, word_ids, counts) CSR triple."""
+	if native and not stochastic:
+		from .. import capi
+		reader = capi.Reader(filepath, batch_size, prefetch=prefetch)
+		if batch_size:
+			return ((b.doc_ptr, b.word_ids, b.counts) for b in reader)
+		batch = next(reader)
+		reader.close()
+		return batch.doc_ptr, batch.word_ids, batch.counts
 	if batch_size:
 		return (_to_csr(batch) for batch in _batches(filepath, batch_size, stochastic, _parse_arrays))
 	return _to_csr(next(_batches(filepath, batch_size, stochastic, _parse_arrays)))
