@@ -26,7 +26,7 @@ for r in rows:
 	total[name] += float(r['Metric Value'].replace(',', '')) / 1e6
 	count[name] += 1
 grand = sum(total.values())
-summary = ['# %s — ncu launch list of `python bench.py --steps 2 --warmup 1 --no-cpu-baseline`' % tag,
+summary = ['# %s — ncu launch list of `python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-extras`' % tag,
 	'(`ncu --metrics gpu__time_duration.sum --clock-control none`; cold-cache, serialised: compare shares)', '',
 	'| kernel | launches | total ms | share | mean ms |', '|---|---:|---:|---:|---:|']
 for name, ms in total.most_common():
@@ -60,32 +60,47 @@ for i, r in enumerate(body):
 		float(g('dram__bytes_read.sum')), float(g('dram__bytes_write.sum')),
 		float(g('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed')), float(g('lts__t_sector_hit_rate.pct')),
 		float(g('smsp__issue_active.avg.pct_of_peak_sustained_active')), g('launch__registers_per_thread')))
-# ---- E-step launch by launch (metrics pass over k_estep_stream only) ----------------------------------------------------
+# ---- E-step launch by launch (metrics pass over the E-step kernels only) ------------------------------------------------
 if traffic:
-	import shutil
+	import json, shutil
 	shutil.copyfile(traffic, os.path.join(ROOT, 'profiles', '%s_estep_traffic.csv' % tag))
 	with open(traffic) as f:
 		trows = list(csv.DictReader([l for l in f if not l.startswith('==')]))
 	per = collections.defaultdict(dict)
+	names = {}
 	for r in trows:
 		per[int(r['ID'])][r['Metric Name']] = (float(r['Metric Value'].replace(',', '')), r['Metric Unit'])
+		names[int(r['ID'])] = r['Kernel Name'].split('(')[0].replace('void ', '').replace('trlda::', '')
 	scale = {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1, 'ms': 1e-3, 'us': 1e-6, 'ns': 1e-9, 's': 1, '%': 1}
-	summary += ['', '## k_estep_stream, launch by launch (%s_estep_traffic.csv)' % tag, '',
-		'`ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sector_hit_rate.pct,'
-		'l1tex__m_xbar2l1tex_read_bytes.sum -k regex:k_estep_stream -c 30 python bench.py --steps 2 --warmup 1`:',
-		'three update_parameters steps of ten trust-region iterations each.  The first E-steps of a step run the full 20 inner',
-		'iterations (21 sweeps of the 4.9 GB of tiles = 103 GB from L2 to the SMs); the later ones start from a converged',
-		'gamma and stop after one inner iteration (2 sweeps).', '',
-		'| launch | ms | HBM read GB | HBM write GB | L2 hit % | L2 -> SM GB | L2 -> SM TB/s |', '|---:|---:|---:|---:|---:|---:|---:|']
-	tot = [0., 0., 0., 0.]
+	# one E-step call = the launches up to the next k_estep_stream launch (the documents too long for the TMEM tile come first)
+	calls, current = [], None
 	for i in sorted(per):
-		m = per[i]
-		v = lambda k: m[k][0] * scale.get(m[k][1], 1)
-		t, rd, wr, l2 = v('gpu__time_duration.sum'), v('dram__bytes_read.sum'), v('dram__bytes_write.sum'), v('l1tex__m_xbar2l1tex_read_bytes.sum')
+		if current is None or names[i].startswith('k_estep_stream'):
+			current = []
+			calls.append(current)
+		current.append(i)
+	summary += ['', '## E-step, call by call (%s_estep_traffic.csv)' % tag, '',
+		'`ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sector_hit_rate.pct,'
+		'l1tex__m_xbar2l1tex_read_bytes.sum -k regex:k_estep -c 130 python bench.py --steps 2 --warmup 1 --no-extras`:',
+		'three update_parameters steps of ten trust-region iterations each; one E-step call = one k_estep_stream launch for the',
+		'documents of more than 192 pairs + one k_estep_tmem launch per tile shape (192 / 160 / 128 columns).  The tile is read',
+		'from HBM once per call whatever the number of inner iterations; it then lives in tensor memory.', '',
+		'| E-step call | launches | ms | HBM read GB | HBM write GB | L2 -> SM GB |', '|---:|---:|---:|---:|---:|---:|']
+	tot = [0., 0., 0., 0.]
+	for c, ids in enumerate(calls):
+		t = rd = wr = l2 = 0.
+		for i in ids:
+			m = per[i]
+			v = lambda k: m[k][0] * scale.get(m[k][1], 1)
+			t += v('gpu__time_duration.sum'); rd += v('dram__bytes_read.sum'); wr += v('dram__bytes_write.sum'); l2 += v('l1tex__m_xbar2l1tex_read_bytes.sum')
 		tot = [tot[0] + t, tot[1] + rd, tot[2] + wr, tot[3] + l2]
-		summary.append('| %d | %.2f | %.2f | %.2f | %.0f | %.1f | %.1f |' % (i, t * 1e3, rd / 1e9, wr / 1e9, m['lts__t_sector_hit_rate.pct'][0], l2 / 1e9, l2 / t / 1e12))
-	n = len(per)
-	summary.append('| mean | %.2f | %.2f | %.2f | | %.1f | %.1f |' % (tot[0] / n * 1e3, tot[1] / n / 1e9, tot[2] / n / 1e9, tot[3] / n / 1e9, tot[3] / tot[0] / 1e12))
+		summary.append('| %d | %d | %.2f | %.2f | %.2f | %.2f |' % (c, len(ids), t * 1e3, rd / 1e9, wr / 1e9, l2 / 1e9))
+	n = len(calls)
+	summary.append('| mean | | %.2f | %.2f | %.2f | %.2f |' % (tot[0] / n * 1e3, tot[1] / n / 1e9, tot[2] / n / 1e9, tot[3] / n / 1e9))
+	with open(os.path.join(ROOT, 'profiles', '%s_estep_traffic.json' % tag), 'w') as f:
+		json.dump({'cfg3/mixed': {
+			'bytes_per_estep': (tot[1] + tot[2]) / n, 'l2_to_sm_bytes_per_estep': tot[3] / n, 'estep_calls': n,
+			'source': 'profiles/%s_estep_traffic.csv: dram__bytes_read.sum + dram__bytes_write.sum summed over the launches of one E-step call, mean over %d calls (three steps of the bench command; cold and warm calls move the same bytes)' % (tag, n)}}, f, indent=1)
 
 with open(os.path.join(ROOT, 'profiles', '%s_summary.md' % tag), 'w') as f:
 	f.write('\n'.join(summary) + '\n')
