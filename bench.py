@@ -397,8 +397,8 @@ def timed_leg(run, w, precision, lam0, batches, steps, warmup, sample_clocks=Fal
 
 def multi_gpu_parity(run):
 	"""The N-rank path against rank 0 alone on the same minibatch, before anything is timed: K=1000, V=20 000, 512
-	documents, T=3, I=20 with the empirical-Bayes updates, both exchange implementations (NVLink peer stores / NCCL
-	all-reduce), both precisions.  fp64 must agree to 1e-11 (sum order), mixed to 1e-4, in the metric of
+	documents, T=3, I=20 with the empirical-Bayes updates, all three exchange implementations (all-gather of the factors +
+	word-sharded M-step, the default; NVLink peer stores; NCCL all-reduce of the dense statistics), both precisions.  fp64 must agree to 1e-11 (sum order), mixed to 1e-4, in the metric of
 	tests/common.py parity_err.  Raises SystemExit if not."""
 	from trlda_b200 import capi
 	from trlda_b200.distributed import init_comm, shard_bounds, shard_documents
@@ -420,7 +420,7 @@ def multi_gpu_parity(run):
 			m1.update_parameters(capi.CSR(ptr, ids, cts), gamma0=g0, **kwargs)
 			single = (m1.lambdas, m1.alpha, m1.eta)
 			m1.close()
-		for mode in ('peer', 'allreduce'):
+		for mode in ('gather', 'peer', 'allreduce'):
 			os.environ['TRLDA_MULTI_GPU'] = mode
 			m = capi.Model('online', V, K, D, .1, .2, device=run.local_rank, precision=precision)
 			m.lambdas = lam0
@@ -652,7 +652,7 @@ def main():
 			'workload': w['desc'], 'global_batch': head['global_batch'], 'docs_per_gpu': B_local, 'pairs_per_gpu': N_local,
 			'minibatches': '%d distinct minibatches of one synthetic corpus (same topics on every rank), one per step: every step sees unseen documents' % num_batches,
 			'precision': args.precision,
-			'parallelism': ('single GPU' if world == 1 else 'the global minibatch sharded over %d GPUs (balanced by pairs); per TR iteration one fused reduce-scatter + M-step + all-gather of beta over NVLink peer memory' % world),
+			'parallelism': ('single GPU' if world == 1 else 'the global minibatch sharded over %d GPUs (balanced by pairs); per TR iteration an all-gather of etheta and the token weights, scatter + M-step + beta-prep on every rank\'s word range, an all-gather of beta (NCCL over NVLink)' % world),
 			'l2': 'no flush needed: every step streams lambda/beta (%.1f GB working set >> 126 MB L2)' % (K * V * (16 + s_bytes) / 1e9)},
 		'clocks': head['clocks'],
 		'e2e': {

@@ -678,10 +678,11 @@ __global__ void __launch_bounds__(NT, (NT == 128 && NCH <= 2 ? 5 : 1)) k_scatter
 		}
 	};
 	int buf = 0;
-	if((int) blockIdx.x < a.V)
-		stage_tokens(0, docs.word_ptr[blockIdx.x], docs.word_ptr[blockIdx.x + 1]);
+	const int w_begin = a.v1 < 0 ? 0 : a.v0, w_end = a.v1 < 0 ? a.V : a.v1;       // this launch's words
+	if(w_begin + (int) blockIdx.x < w_end)
+		stage_tokens(0, docs.word_ptr[w_begin + blockIdx.x], docs.word_ptr[w_begin + blockIdx.x + 1]);
 	__syncthreads();
-	for(int w = blockIdx.x; w < a.V; w += gridDim.x) {
+	for(int w = w_begin + blockIdx.x; w < w_end; w += gridDim.x) {
 		const int64_t base = (int64_t) w * K;
 		float4 bcol[NCH];
 		double lp[NCH][4];
@@ -707,7 +708,7 @@ __global__ void __launch_bounds__(NT, (NT == 128 && NCH <= 2 ? 5 : 1)) k_scatter
 		// processed (one cooperative round of the dependent loads tok_src -> weight instead of one per token group);
 		// now the next word's are requested
 		const int wn = w + gridDim.x;
-		if(wn < a.V)
+		if(wn < w_end)
 			stage_tokens(buf ^ 1, docs.word_ptr[wn], docs.word_ptr[wn + 1]);
 		for(int ts = t0; ts < t1; ts += NT) {
 			if(ts > t0) {                                              // words with more than NT tokens: restage in place
@@ -826,7 +827,10 @@ static void launch_scatter_t(const ScatterArgs& a, const DeviceDocs& docs, cudaS
 
 void launch_scatter(const ScatterArgs& a, const DeviceDocs& docs, cudaStream_t s) {
 	if(a.etheta_elem == 4 && a.beta_elem == 4 && a.K % 4 == 0 && a.K <= 4096) {
-		const int grid = std::min(a.V, sm_count() * 64);
+		const int words = a.v1 < 0 ? a.V : a.v1 - a.v0;
+		if(words <= 0)
+			return;
+		const int grid = std::min(words, sm_count() * 64);
 		const int chunks = a.K / 4;
 		if(chunks <= 128) k_scatter_vec<128, 1, 4><<<grid, 128, 0, s>>>(a, docs);
 		else if(chunks <= 256) k_scatter_vec<128, 2, 4><<<grid, 128, 0, s>>>(a, docs);

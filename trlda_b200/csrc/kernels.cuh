@@ -151,6 +151,7 @@ struct ScatterArgs {
 	const double* psi_rows = nullptr; // psi of the NEW row sums
 	bool write_beta = false;
 	double* psi_partials = nullptr;   // V values: sum_k psi(lambda_new[k, w]) (for the eta update) or null
+	int v0 = 0, v1 = -1;              // word range handled by this launch (v1 < 0: all words); the float32 vector kernel only
 };
 void launch_scatter(const ScatterArgs& a, const DeviceDocs& docs, cudaStream_t s);
 

@@ -103,6 +103,9 @@ struct NcclApi {
 	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
 	ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
 	ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*GroupStart)() = nullptr;
+	ncclResult_t (*GroupEnd)() = nullptr;
 	const char* (*GetErrorString)(ncclResult_t) = nullptr;
 	bool ok = false;
 };
@@ -125,7 +128,11 @@ NcclApi& nccl_api() {
 		api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(api.handle, "ncclAllReduce"));
 		api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(api.handle, "ncclGetErrorString"));
 		api.AllGather = reinterpret_cast<decltype(api.AllGather)>(dlsym(api.handle, "ncclAllGather"));
-		api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.AllGather && api.GetErrorString;
+		api.Broadcast = reinterpret_cast<decltype(api.Broadcast)>(dlsym(api.handle, "ncclBroadcast"));
+		api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(dlsym(api.handle, "ncclGroupStart"));
+		api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(dlsym(api.handle, "ncclGroupEnd"));
+		api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.AllGather && api.GetErrorString &&
+		         api.Broadcast && api.GroupStart && api.GroupEnd;
 	});
 	return api;
 }
@@ -211,8 +218,23 @@ struct trlda_model {
 	int64_t len_gt[4] = {0, 0, 0, 0};
 	bool force_generic = false;
 	// parked resident minibatches (trlda_upload_docs_slot / trlda_select_docs): the live buffers are swapped with a slot
+	// Multi-GPU "gather" exchange (default for the mixed mode): every rank holds the token list of the WHOLE minibatch,
+	// sorted by word and restricted to the words it owns; per trust-region iteration the ranks all-gather etheta and the
+	// token weights (43 MB at cfg-3), every rank scatters + blends + prepares beta for ITS word range with the single-GPU
+	// kernel, and the ranks all-gather the new beta.  No K x V partial statistics cross NVLink.
+	struct GlobalDocs {
+		bool ready = false;
+		std::vector<int64_t> shard_B, shard_N, doc_off, tok_off;      // per rank: documents, pairs, and where they start
+		int64_t B = 0, N = 0;
+		DevBuf len, ids, word_ptr, tok_doc, tok_src, etheta32, weight;
+		DeviceDocs view;                                               // word_ptr / tok_doc / tok_src of the global batch
+	};
+	GlobalDocs gdocs;
+	bool use_gather = true;                    // TRLDA_MULTI_GPU=gather (default) | peer | allreduce
+	PinnedBuf gstage;
 	struct DocSlot {
 		bool used = false;
+		GlobalDocs gdocs;
 		DeviceDocs docs;
 		DevBuf b_doc_ptr, b_word_ids, b_counts, b_word_ptr, b_tok_doc, b_tok_src, b_order;
 		std::vector<Bucket> buckets;
@@ -453,10 +475,13 @@ void swap_with_slot(trlda_model* m, trlda_model::DocSlot& slot) {
 	std::swap(m->b_tok_src, slot.b_tok_src);
 	std::swap(m->b_order, slot.b_order);
 	std::swap(m->buckets, slot.buckets);
+	std::swap(m->gdocs, slot.gdocs);
 	std::swap(m->len_gt, slot.len_gt);
 	std::swap(m->docs_total_count, slot.docs_total_count);
 	std::swap(m->global_B, slot.global_B);
 }
+
+int build_global_docs(trlda_model* m, const int64_t* s_ptr, int64_t B, int64_t N);
 
 // ---- minibatch upload: CSR + word-sorted token list ---------------------------------------------------------------
 int upload_docs(trlda_model* m, const trlda_docs* docs) {
@@ -652,10 +677,172 @@ int upload_docs(trlda_model* m, const trlda_docs* docs) {
 	CUDA_TRY(m, m->doc_stat.ensure(kb));
 	CUDA_TRY(m, m->weight.ensure(sizeof(double) * std::max<int64_t>(N, 1)));
 	CUDA_TRY(m, m->iterations.ensure(sizeof(int32_t) * std::max<int64_t>(B, 1)));
+	m->gdocs.ready = false;
+	if(m->nranks > 1 && m->use_gather && m->beta_elem == 4 && m->K % 4 == 0 && m->K <= 4096)
+		TRY(build_global_docs(m, s_ptr, B, N));
 	if(host_timing)
 		fprintf(stderr, "[trlda] upload_docs: wait for stream %.2f ms, host packing (copy + counting sort + buckets) %.2f ms, total incl. H2D enqueue %.2f ms\n",
 		        t_sync, t_host - t_sync, ms_since(t_begin));
 	return TRLDA_OK;
+}
+
+// ---- multi-GPU gather exchange: the token list of the whole minibatch, word-sorted, for this rank's words --------
+int word_begin(const trlda_model* m, int rank) { return (int) ((int64_t) m->V * rank / m->nranks); }
+
+// `count` elements of `type` from every rank's segment of `buf` (segment r starts at element off[r], has n[r] elements)
+int gather_segments(trlda_model* m, void* buf, const std::vector<int64_t>& off, const std::vector<int64_t>& n, size_t elem,
+                    ncclDataType_t type) {
+	NCCL_TRY(m, nccl_api().GroupStart());
+	for(int r = 0; r < m->nranks; ++r)
+		if(n[r] > 0) {
+			char* seg = static_cast<char*>(buf) + (size_t) off[r] * elem;
+			NCCL_TRY(m, nccl_api().Broadcast(seg, seg, (size_t) n[r], type, r, m->comm, m->stream));
+		}
+	NCCL_TRY(m, nccl_api().GroupEnd());
+	return TRLDA_OK;
+}
+
+int build_global_docs(trlda_model* m, const int64_t* s_ptr, int64_t B, int64_t N) {
+	trlda_model::GlobalDocs& g = m->gdocs;
+	g.ready = false;
+	const int R = m->nranks;
+	// sizes of all shards
+	TRY(ensure_small(m));
+	{
+		int64_t* h = m->readback.as<int64_t>();
+		for(int i = 0; i < 2 * R; ++i)
+			h[i] = 0;
+		h[2 * m->rank] = B;
+		h[2 * m->rank + 1] = N;
+		CUDA_TRY(m, cudaMemcpyAsync(m->scalars.p, h, 2 * R * sizeof(int64_t), cudaMemcpyHostToDevice, m->stream));
+		TRY(allreduce(m, m->scalars.p, 2 * R, ncclInt64));
+		CUDA_TRY(m, cudaMemcpyAsync(h, m->scalars.p, 2 * R * sizeof(int64_t), cudaMemcpyDeviceToHost, m->stream));
+		CUDA_TRY(m, cudaStreamSynchronize(m->stream));
+		g.shard_B.assign(R, 0); g.shard_N.assign(R, 0); g.doc_off.assign(R, 0); g.tok_off.assign(R, 0);
+		g.B = g.N = 0;
+		for(int r = 0; r < R; ++r) {
+			g.shard_B[r] = h[2 * r];
+			g.shard_N[r] = h[2 * r + 1];
+			g.doc_off[r] = g.B;
+			g.tok_off[r] = g.N;
+			g.B += g.shard_B[r];
+			g.N += g.shard_N[r];
+		}
+	}
+	if(g.N > INT32_MAX)
+		return fail(m, TRLDA_ERR_ARG, "Too many (word, count) pairs in one minibatch.");
+	CUDA_TRY(m, g.len.ensure(sizeof(int32_t) * std::max<int64_t>(g.B, 1)));
+	CUDA_TRY(m, g.ids.ensure(sizeof(int32_t) * std::max<int64_t>(g.N, 1)));
+	CUDA_TRY(m, m->gstage.ensure(sizeof(int32_t) * (size_t) (std::max<int64_t>(g.B, 1) + 3 * std::max<int64_t>(g.N, 1) + m->V + 2)));
+	int32_t* h_len = m->gstage.as<int32_t>();
+	int32_t* h_ids = h_len + std::max<int64_t>(g.B, 1);
+	for(int64_t d = 0; d < B; ++d)
+		h_len[g.doc_off[m->rank] + d] = (int32_t) (s_ptr[d + 1] - s_ptr[d]);
+	if(B)
+		CUDA_TRY(m, cudaMemcpyAsync(g.len.as<int32_t>() + g.doc_off[m->rank], h_len + g.doc_off[m->rank], sizeof(int32_t) * B,
+		                            cudaMemcpyHostToDevice, m->stream));
+	if(N)
+		CUDA_TRY(m, cudaMemcpyAsync(g.ids.as<int32_t>() + g.tok_off[m->rank], m->b_word_ids.p, sizeof(int32_t) * N,
+		                            cudaMemcpyDeviceToDevice, m->stream));
+	TRY(gather_segments(m, g.len.p, g.doc_off, g.shard_B, sizeof(int32_t), ncclInt32));
+	TRY(gather_segments(m, g.ids.p, g.tok_off, g.shard_N, sizeof(int32_t), ncclInt32));
+	if(g.B)
+		CUDA_TRY(m, cudaMemcpyAsync(h_len, g.len.p, sizeof(int32_t) * g.B, cudaMemcpyDeviceToHost, m->stream));
+	if(g.N)
+		CUDA_TRY(m, cudaMemcpyAsync(h_ids, g.ids.p, sizeof(int32_t) * g.N, cudaMemcpyDeviceToHost, m->stream));
+	CUDA_TRY(m, cudaStreamSynchronize(m->stream));
+	// word-sorted token list of this rank's words [v0, v1): stable counting sort over the global token stream, the
+	// threads taking contiguous document ranges (as in ensure_csc)
+	const int v0 = word_begin(m, m->rank), v1 = word_begin(m, m->rank + 1), nv = v1 - v0;
+	int32_t* h_tdoc = h_ids + std::max<int64_t>(g.N, 1);
+	int32_t* h_tsrc = h_tdoc + std::max<int64_t>(g.N, 1);
+	int32_t* h_wptr = h_tsrc + std::max<int64_t>(g.N, 1);
+	std::vector<int64_t> gptr((size_t) g.B + 1, 0);
+	for(int64_t d = 0; d < g.B; ++d)
+		gptr[d + 1] = gptr[d] + h_len[d];
+	const int T = (int) std::max(1u, std::min(8u, std::min(std::thread::hardware_concurrency(), (unsigned) (g.N / 65536 + 1))));
+	std::vector<int64_t> cut(T + 1, g.B);
+	cut[0] = 0;
+	for(int t = 1; t < T; ++t)
+		cut[t] = std::lower_bound(gptr.begin(), gptr.begin() + g.B, g.N * t / T) - gptr.begin();
+	std::vector<std::vector<int32_t>> hist(T);
+	auto run = [&](auto&& fn) {
+		std::vector<std::thread> pool;
+		for(int t = 1; t < T; ++t)
+			pool.emplace_back(fn, t);
+		fn(0);
+		for(auto& th : pool)
+			th.join();
+	};
+	run([&](int t) {
+		hist[t].assign((size_t) std::max(nv, 1), 0);
+		int32_t* h = hist[t].data();
+		for(int64_t i = gptr[cut[t]]; i < gptr[cut[t + 1]]; ++i) {
+			const int32_t w = h_ids[i];
+			if(w >= v0 && w < v1)
+				h[w - v0]++;
+		}
+	});
+	int32_t total = 0;
+	for(int w = 0; w <= v0; ++w)
+		h_wptr[w] = 0;
+	for(int w = v0; w < v1; ++w) {
+		h_wptr[w] = total;
+		for(int t = 0; t < T; ++t) {
+			const int32_t c = hist[t][w - v0];
+			hist[t][w - v0] = total;
+			total += c;
+		}
+	}
+	for(int w = v1; w <= m->V; ++w)
+		h_wptr[w] = total;
+	const int64_t own = total;
+	run([&](int t) {
+		int32_t* cursor = hist[t].data();
+		for(int64_t d = cut[t]; d < cut[t + 1]; ++d)
+			for(int64_t i = gptr[d]; i < gptr[d + 1]; ++i) {
+				const int32_t w = h_ids[i];
+				if(w >= v0 && w < v1) {
+					const int32_t pos = cursor[w - v0]++;
+					h_tdoc[pos] = (int32_t) d;
+					h_tsrc[pos] = (int32_t) i;
+				}
+			}
+	});
+	CUDA_TRY(m, g.word_ptr.ensure(sizeof(int32_t) * ((size_t) m->V + 1)));
+	CUDA_TRY(m, g.tok_doc.ensure(sizeof(int32_t) * std::max<int64_t>(own, 1)));
+	CUDA_TRY(m, g.tok_src.ensure(sizeof(int32_t) * std::max<int64_t>(own, 1)));
+	CUDA_TRY(m, g.etheta32.ensure(sizeof(float) * (size_t) m->K * std::max<int64_t>(g.B, 1)));
+	CUDA_TRY(m, g.weight.ensure(sizeof(double) * std::max<int64_t>(g.N, 1)));
+	CUDA_TRY(m, cudaMemcpyAsync(g.word_ptr.p, h_wptr, sizeof(int32_t) * ((size_t) m->V + 1), cudaMemcpyHostToDevice, m->stream));
+	if(own) {
+		CUDA_TRY(m, cudaMemcpyAsync(g.tok_doc.p, h_tdoc, sizeof(int32_t) * own, cudaMemcpyHostToDevice, m->stream));
+		CUDA_TRY(m, cudaMemcpyAsync(g.tok_src.p, h_tsrc, sizeof(int32_t) * own, cudaMemcpyHostToDevice, m->stream));
+	}
+	CUDA_TRY(m, cudaStreamSynchronize(m->stream));       // the pinned staging area is reused by the next upload
+	g.view = DeviceDocs{};
+	g.view.B = g.B;
+	g.view.N = g.N;
+	g.view.word_ptr = g.word_ptr.as<int32_t>();
+	g.view.tok_doc = g.tok_doc.as<int32_t>();
+	g.view.tok_src = g.tok_src.as<int32_t>();
+	m->stats.h2d_bytes += sizeof(int32_t) * (size_t) (m->V + 1 + 2 * own + B);
+	m->stats.d2h_bytes += sizeof(int32_t) * (size_t) (g.B + g.N);
+	g.ready = true;
+	return TRLDA_OK;
+}
+
+// where the E-step leaves exp(psi(gamma)) (float32) and the token weights: in the gather exchange straight into this
+// rank's segment of the global arrays
+float* estep_etheta32(trlda_model* m) {
+	if(m->gdocs.ready)
+		return m->gdocs.etheta32.as<float>() + (size_t) m->gdocs.doc_off[m->rank] * m->K;
+	return m->etheta32.as<float>();
+}
+double* estep_weight(trlda_model* m) {
+	if(m->gdocs.ready)
+		return m->gdocs.weight.as<double>() + m->gdocs.tok_off[m->rank];
+	return m->weight.as<double>();
 }
 
 // where the initial gamma of an E-step comes from
@@ -694,8 +881,8 @@ int run_estep(trlda_model* m, GammaSource src, const double* host_gamma, int max
 	a.alpha = m->d_alpha.as<double>();
 	a.gamma = m->gamma.as<double>();
 	a.etheta = m->etheta.as<double>();
-	a.etheta32 = m->beta_elem == 4 ? m->etheta32.as<float>() : nullptr;
-	a.weight = m->weight.as<double>();
+	a.etheta32 = m->beta_elem == 4 ? estep_etheta32(m) : nullptr;
+	a.weight = estep_weight(m);
 	a.doc_stat = m->doc_stat.as<double>();
 	a.iterations = m->iterations.as<int32_t>();
 	a.max_iter = max_iter;
@@ -882,9 +1069,9 @@ int run_scatter_dense(trlda_model* m, bool reduce_over_ranks = true, bool for_pe
 	ScatterArgs a;
 	a.K = m->K;
 	a.V = m->V;
-	a.etheta = m->beta_elem == 4 ? m->etheta32.p : m->etheta.p;
+	a.etheta = m->beta_elem == 4 ? (void*) estep_etheta32(m) : m->etheta.p;
 	a.etheta_elem = m->beta_elem == 4 ? 4 : 8;
-	a.weight = m->weight.as<double>();
+	a.weight = estep_weight(m);
 	a.beta = m->beta.p;
 	a.beta_elem = m->beta_elem;
 	a.sstats = m->sstats.as<double>();
@@ -938,6 +1125,66 @@ int run_mstep(trlda_model* m, const MStepCoef& coef, const double* prime, double
 		Launch l(m, KK_MISC);
 		launch_rows_update(coef.mode == MSTEP_BATCH ? nullptr : m->rows_prev.as<double>(), m->rows_stat.as<double>(), a, b, c,
 		                   m->K, m->rows.as<double>(), m->psi_rows.as<double>(), m->stream);
+	}
+	if(m->nranks > 1 && m->gdocs.ready && !force_dense) {
+		// gather exchange: (1) every rank receives all documents' etheta and token weights; (2) the single-GPU kernel
+		// (scatter + blend + beta-prep) runs on this rank's words over the tokens of ALL documents; (3) the ranks
+		// exchange their slices of the new beta (and, when the caller needs lambda afterwards, of lambda)
+		trlda_model::GlobalDocs& g = m->gdocs;
+		const int v0 = word_begin(m, m->rank), v1 = word_begin(m, m->rank + 1);
+		{
+			std::vector<int64_t> eoff(m->nranks), en(m->nranks);
+			for(int r = 0; r < m->nranks; ++r) {
+				eoff[r] = g.doc_off[r] * m->K;
+				en[r] = g.shard_B[r] * m->K;
+			}
+			nvtxRangePushA("exchange: all-gather etheta, weights");
+			TRY(gather_segments(m, g.etheta32.p, eoff, en, sizeof(float), ncclFloat));
+			TRY(gather_segments(m, g.weight.p, g.tok_off, g.shard_N, sizeof(double), ncclDouble));
+			nvtxRangePop();
+		}
+		if(want_psi_partials)
+			CUDA_TRY(m, cudaMemsetAsync(m->vpartials.p, 0, sizeof(double) * m->V, m->stream));
+		{
+			ScatterArgs sa;
+			sa.K = m->K;
+			sa.V = m->V;
+			sa.etheta = g.etheta32.p;
+			sa.etheta_elem = 4;
+			sa.weight = g.weight.as<double>();
+			sa.beta = m->beta.p;
+			sa.beta_elem = m->beta_elem;
+			sa.fused = true;
+			sa.coef = coef;
+			sa.lambda_prime = prime;
+			sa.lambda = target;
+			sa.psi_rows = m->psi_rows.as<double>();
+			sa.write_beta = write_beta;
+			sa.psi_partials = want_psi_partials ? m->vpartials.as<double>() : nullptr;
+			sa.v0 = v0;
+			sa.v1 = v1;
+			Launch l(m, KK_SCATTER_MSTEP);
+			launch_scatter(sa, g.view, m->stream);
+		}
+		TRY(check_launch(m, "mstep (word shard)"));
+		{
+			std::vector<int64_t> woff(m->nranks), wn(m->nranks);
+			for(int r = 0; r < m->nranks; ++r) {
+				woff[r] = (int64_t) word_begin(m, r) * m->K;
+				wn[r] = (int64_t) (word_begin(m, r + 1) - word_begin(m, r)) * m->K;
+			}
+			nvtxRangePushA("exchange: all-gather beta / lambda");
+			if(write_beta)
+				TRY(gather_segments(m, m->beta.p, woff, wn, sizeof(float), ncclFloat));
+			if(broadcast_lambda)
+				TRY(gather_segments(m, target, woff, wn, sizeof(double), ncclDouble));
+			nvtxRangePop();
+		}
+		if(want_psi_partials)
+			TRY(allreduce(m, m->vpartials.p, m->V, ncclDouble));
+		m->beta_valid = write_beta;
+		m->lambda_sharded = !broadcast_lambda;
+		return TRLDA_OK;
 	}
 	if(m->nranks > 1 && m->peer_ready && m->use_peer && !force_dense && m->K % 4 == 0) {
 		// fused path over NVLink peer memory: local scatter, barrier, then one kernel per rank that pulls every
@@ -1003,9 +1250,9 @@ int run_mstep(trlda_model* m, const MStepCoef& coef, const double* prime, double
 		ScatterArgs sa;
 		sa.K = m->K;
 		sa.V = m->V;
-		sa.etheta = m->beta_elem == 4 ? m->etheta32.p : m->etheta.p;
+		sa.etheta = m->beta_elem == 4 ? (void*) estep_etheta32(m) : m->etheta.p;
 		sa.etheta_elem = m->beta_elem == 4 ? 4 : 8;
-		sa.weight = m->weight.as<double>();
+		sa.weight = estep_weight(m);
 		sa.beta = m->beta.p;
 		sa.beta_elem = m->beta_elem;
 		sa.fused = true;
@@ -1627,7 +1874,16 @@ void trlda_destroy(trlda_model* m) {
 	                  &m->sample_cdf, &m->sample_tokens, &m->sample_counts, &m->sample_lengths};
 	for(DevBuf* b : bufs)
 		b->release();
+	{
+		DevBuf* gb[] = {&m->gdocs.len, &m->gdocs.ids, &m->gdocs.word_ptr, &m->gdocs.tok_doc, &m->gdocs.tok_src, &m->gdocs.etheta32, &m->gdocs.weight};
+		for(DevBuf* b : gb)
+			b->release();
+		m->gstage.release();
+	}
 	for(auto& slot : m->slots) {
+		DevBuf* gb[] = {&slot.gdocs.len, &slot.gdocs.ids, &slot.gdocs.word_ptr, &slot.gdocs.tok_doc, &slot.gdocs.tok_src, &slot.gdocs.etheta32, &slot.gdocs.weight};
+		for(DevBuf* b : gb)
+			b->release();
 		DevBuf* sb[] = {&slot.b_doc_ptr, &slot.b_word_ids, &slot.b_counts, &slot.b_word_ptr, &slot.b_tok_doc, &slot.b_tok_src, &slot.b_order};
 		for(DevBuf* b : sb)
 			b->release();
@@ -2056,8 +2312,10 @@ int trlda_comm_init(trlda_model* m, const void* id_bytes, int rank, int nranks) 
 	NCCL_TRY(m, nccl_api().CommInitRank(&m->comm, nranks, id, rank));
 	m->rank = rank;
 	m->nranks = nranks;
-	if(const char* mode = getenv("TRLDA_MULTI_GPU"))
+	if(const char* mode = getenv("TRLDA_MULTI_GPU")) {
 		m->use_peer = strcmp(mode, "allreduce") != 0;
+		m->use_gather = strcmp(mode, "gather") == 0;
+	}
 	if(!m->use_peer || nranks > TRLDA_MAX_RANKS)
 		return TRLDA_OK;
 
