@@ -225,6 +225,7 @@ struct trlda_model {
 	struct GlobalDocs {
 		bool ready = false;
 		std::vector<int64_t> shard_B, shard_N, doc_off, tok_off;      // per rank: documents, pairs, and where they start
+		std::vector<int64_t> pad_B, pad_N;                             // segment sizes (padded to the largest shard)
 		int64_t B = 0, N = 0;
 		DevBuf len, ids, word_ptr, tok_doc, tok_src, etheta32, weight;
 		DeviceDocs view;                                               // word_ptr / tok_doc / tok_src of the global batch
@@ -692,6 +693,15 @@ int word_begin(const trlda_model* m, int rank) { return (int) ((int64_t) m->V * 
 // `count` elements of `type` from every rank's segment of `buf` (segment r starts at element off[r], has n[r] elements)
 int gather_segments(trlda_model* m, void* buf, const std::vector<int64_t>& off, const std::vector<int64_t>& n, size_t elem,
                     ncclDataType_t type) {
+	// equal, contiguous segments: ONE bandwidth-optimal all-gather in place; else one broadcast per rank in a group
+	bool regular = true;
+	for(int r = 0; r < m->nranks; ++r)
+		regular = regular && n[r] == n[0] && off[r] == (int64_t) r * n[0];
+	if(regular) {
+		if(n[0] > 0)
+			NCCL_TRY(m, nccl_api().AllGather(static_cast<char*>(buf) + (size_t) off[m->rank] * elem, buf, (size_t) n[0], type, m->comm, m->stream));
+		return TRLDA_OK;
+	}
 	NCCL_TRY(m, nccl_api().GroupStart());
 	for(int r = 0; r < m->nranks; ++r)
 		if(n[r] > 0) {
@@ -719,15 +729,24 @@ int build_global_docs(trlda_model* m, const int64_t* s_ptr, int64_t B, int64_t N
 		CUDA_TRY(m, cudaMemcpyAsync(h, m->scalars.p, 2 * R * sizeof(int64_t), cudaMemcpyDeviceToHost, m->stream));
 		CUDA_TRY(m, cudaStreamSynchronize(m->stream));
 		g.shard_B.assign(R, 0); g.shard_N.assign(R, 0); g.doc_off.assign(R, 0); g.tok_off.assign(R, 0);
-		g.B = g.N = 0;
+		g.pad_B.assign(R, 0); g.pad_N.assign(R, 0);
+		int64_t max_B = 0, max_N = 0;
 		for(int r = 0; r < R; ++r) {
 			g.shard_B[r] = h[2 * r];
 			g.shard_N[r] = h[2 * r + 1];
-			g.doc_off[r] = g.B;
-			g.tok_off[r] = g.N;
-			g.B += g.shard_B[r];
-			g.N += g.shard_N[r];
+			max_B = std::max(max_B, g.shard_B[r]);
+			max_N = std::max(max_N, g.shard_N[r]);
 		}
+		// every rank's segment of the global document / token index space is padded to the largest shard, so that the
+		// per-iteration exchanges are plain all-gathers; the padding is never referenced by a token
+		for(int r = 0; r < R; ++r) {
+			g.doc_off[r] = r * max_B;
+			g.tok_off[r] = r * max_N;
+			g.pad_B[r] = max_B;
+			g.pad_N[r] = max_N;
+		}
+		g.B = R * max_B;
+		g.N = R * max_N;
 	}
 	if(g.N > INT32_MAX)
 		return fail(m, TRLDA_ERR_ARG, "Too many (word, count) pairs in one minibatch.");
@@ -736,16 +755,18 @@ int build_global_docs(trlda_model* m, const int64_t* s_ptr, int64_t B, int64_t N
 	CUDA_TRY(m, m->gstage.ensure(sizeof(int32_t) * (size_t) (std::max<int64_t>(g.B, 1) + 3 * std::max<int64_t>(g.N, 1) + m->V + 2)));
 	int32_t* h_len = m->gstage.as<int32_t>();
 	int32_t* h_ids = h_len + std::max<int64_t>(g.B, 1);
-	for(int64_t d = 0; d < B; ++d)
-		h_len[g.doc_off[m->rank] + d] = (int32_t) (s_ptr[d + 1] - s_ptr[d]);
-	if(B)
-		CUDA_TRY(m, cudaMemcpyAsync(g.len.as<int32_t>() + g.doc_off[m->rank], h_len + g.doc_off[m->rank], sizeof(int32_t) * B,
+	for(int64_t d = 0; d < g.pad_B[m->rank]; ++d)
+		h_len[g.doc_off[m->rank] + d] = d < B ? (int32_t) (s_ptr[d + 1] - s_ptr[d]) : 0;
+	if(g.pad_B[m->rank])
+		CUDA_TRY(m, cudaMemcpyAsync(g.len.as<int32_t>() + g.doc_off[m->rank], h_len + g.doc_off[m->rank], sizeof(int32_t) * g.pad_B[m->rank],
 		                            cudaMemcpyHostToDevice, m->stream));
+	if(g.pad_N[m->rank])
+		CUDA_TRY(m, cudaMemsetAsync(g.ids.as<int32_t>() + g.tok_off[m->rank], 0xff, sizeof(int32_t) * g.pad_N[m->rank], m->stream));   // -1: no word
 	if(N)
 		CUDA_TRY(m, cudaMemcpyAsync(g.ids.as<int32_t>() + g.tok_off[m->rank], m->b_word_ids.p, sizeof(int32_t) * N,
 		                            cudaMemcpyDeviceToDevice, m->stream));
-	TRY(gather_segments(m, g.len.p, g.doc_off, g.shard_B, sizeof(int32_t), ncclInt32));
-	TRY(gather_segments(m, g.ids.p, g.tok_off, g.shard_N, sizeof(int32_t), ncclInt32));
+	TRY(gather_segments(m, g.len.p, g.doc_off, g.pad_B, sizeof(int32_t), ncclInt32));
+	TRY(gather_segments(m, g.ids.p, g.tok_off, g.pad_N, sizeof(int32_t), ncclInt32));
 	if(g.B)
 		CUDA_TRY(m, cudaMemcpyAsync(h_len, g.len.p, sizeof(int32_t) * g.B, cudaMemcpyDeviceToHost, m->stream));
 	if(g.N)
@@ -757,14 +778,21 @@ int build_global_docs(trlda_model* m, const int64_t* s_ptr, int64_t B, int64_t N
 	int32_t* h_tdoc = h_ids + std::max<int64_t>(g.N, 1);
 	int32_t* h_tsrc = h_tdoc + std::max<int64_t>(g.N, 1);
 	int32_t* h_wptr = h_tsrc + std::max<int64_t>(g.N, 1);
+	// gptr[d] .. gptr[d] + len[d]: the tokens of (padded) global document d; a rank's documents are contiguous from tok_off
 	std::vector<int64_t> gptr((size_t) g.B + 1, 0);
-	for(int64_t d = 0; d < g.B; ++d)
-		gptr[d + 1] = gptr[d] + h_len[d];
+	for(int r = 0; r < R; ++r) {
+		int64_t at = g.tok_off[r];
+		for(int64_t d = g.doc_off[r]; d < g.doc_off[r] + g.pad_B[r]; ++d) {
+			gptr[d] = at;
+			at += h_len[d];
+		}
+	}
+	gptr[g.B] = g.N;
 	const int T = (int) std::max(1u, std::min(8u, std::min(std::thread::hardware_concurrency(), (unsigned) (g.N / 65536 + 1))));
 	std::vector<int64_t> cut(T + 1, g.B);
 	cut[0] = 0;
 	for(int t = 1; t < T; ++t)
-		cut[t] = std::lower_bound(gptr.begin(), gptr.begin() + g.B, g.N * t / T) - gptr.begin();
+		cut[t] = g.B * t / T;
 	std::vector<std::vector<int32_t>> hist(T);
 	auto run = [&](auto&& fn) {
 		std::vector<std::thread> pool;
@@ -777,11 +805,12 @@ int build_global_docs(trlda_model* m, const int64_t* s_ptr, int64_t B, int64_t N
 	run([&](int t) {
 		hist[t].assign((size_t) std::max(nv, 1), 0);
 		int32_t* h = hist[t].data();
-		for(int64_t i = gptr[cut[t]]; i < gptr[cut[t + 1]]; ++i) {
-			const int32_t w = h_ids[i];
-			if(w >= v0 && w < v1)
-				h[w - v0]++;
-		}
+		for(int64_t d = cut[t]; d < cut[t + 1]; ++d)
+			for(int64_t i = gptr[d]; i < gptr[d] + h_len[d]; ++i) {
+				const int32_t w = h_ids[i];
+				if(w >= v0 && w < v1)
+					h[w - v0]++;
+			}
 	});
 	int32_t total = 0;
 	for(int w = 0; w <= v0; ++w)
@@ -800,7 +829,7 @@ int build_global_docs(trlda_model* m, const int64_t* s_ptr, int64_t B, int64_t N
 	run([&](int t) {
 		int32_t* cursor = hist[t].data();
 		for(int64_t d = cut[t]; d < cut[t + 1]; ++d)
-			for(int64_t i = gptr[d]; i < gptr[d + 1]; ++i) {
+			for(int64_t i = gptr[d]; i < gptr[d] + h_len[d]; ++i) {
 				const int32_t w = h_ids[i];
 				if(w >= v0 && w < v1) {
 					const int32_t pos = cursor[w - v0]++;
@@ -1136,11 +1165,11 @@ int run_mstep(trlda_model* m, const MStepCoef& coef, const double* prime, double
 			std::vector<int64_t> eoff(m->nranks), en(m->nranks);
 			for(int r = 0; r < m->nranks; ++r) {
 				eoff[r] = g.doc_off[r] * m->K;
-				en[r] = g.shard_B[r] * m->K;
+				en[r] = g.pad_B[r] * m->K;
 			}
 			nvtxRangePushA("exchange: all-gather etheta, weights");
 			TRY(gather_segments(m, g.etheta32.p, eoff, en, sizeof(float), ncclFloat));
-			TRY(gather_segments(m, g.weight.p, g.tok_off, g.shard_N, sizeof(double), ncclDouble));
+			TRY(gather_segments(m, g.weight.p, g.tok_off, g.pad_N, sizeof(double), ncclDouble));
 			nvtxRangePop();
 		}
 		if(want_psi_partials)
