@@ -216,7 +216,8 @@ TRLDA_API const char* trlda_reader_last_error(const trlda_reader* r);
 
 /* device special functions evaluated on n host values (test hook pinning the in-kernel psi / psi' / lgamma
  * against python/tests/utils_test.py:33-51): which = 0 digamma fp64, 1 trigamma fp64, 2 lgamma fp64,
- * 3 exp(digamma) as evaluated in mixed-precision mode, 4 exp(digamma) as evaluated in fp64 mode. */
+ * 3 exp(digamma) as evaluated in mixed-precision mode (beta-prep), 4 exp(digamma) as evaluated in fp64 mode,
+ * 5 exp(digamma) as evaluated inside the mixed-mode E-step kernel (exp_digamma_lean). */
 TRLDA_API int trlda_device_special(int device, int which, const double* x, int64_t n, double* out);
 
 /* host special functions used by the Newton steps: polygamma(n, x) of utils.cpp:107-111 (n = 0, 1, 2) */

@@ -55,6 +55,12 @@ def test_device_exp_digamma_variants(capi):
 	ok = want > 1e-300
 	assert np.max(np.abs(capi.device_special(4, x)[ok] - want[ok]) / want[ok]) < 5e-13
 	assert np.max(np.abs(capi.device_special(3, x)[ok] - want[ok]) / want[ok]) < 1e-10
+	# the branch-free evaluation inside the mixed-mode E-step kernel (Estrin polynomials, degree-9 exp): 2e-11
+	assert np.max(np.abs(capi.device_special(5, x)[ok] - want[ok]) / want[ok]) < 1e-10
+	dense = np.exp(np.random.default_rng(0).uniform(np.log(1e-3), np.log(1e5), size=20000))
+	exact = capi.device_special(4, dense)
+	big = exact > 1e-290          # below, the kernel's evaluation flushes to zero (exponent patch); float32 underflows at 1e-45
+	assert np.max(np.abs(capi.device_special(5, dense)[big] - exact[big]) / exact[big]) < 1e-10
 
 
 # ---- E-step ----------------------------------------------------------------------------------------------------------

@@ -39,6 +39,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 
 namespace trlda {
 
@@ -131,6 +132,7 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
 
 
 constexpr int kTmemBlocks = 4;     // column blocks (64 values each) of a thread's tile kept in TMEM: 8 warps x 256 columns
+constexpr int kTmemMaxBlocks = 6;  // widest tile shape: 6 blocks = documents of up to 192 pairs
 
 }  // namespace
 
@@ -143,7 +145,7 @@ __host__ __device__ constexpr TmemSmem tmem_smem_layout(int C, int NU, int WG) {
 	const int NJ = 32 * NU, ROWS = 64 * WG;
 	TmemSmem L{};
 	size_t o = 0;
-	const int NS = NU < 3 ? NU : 3;
+	const int NS = 3;
 	L.ring = o; o += (size_t) NS * 32 * ROWS * 4;                  // landing ring: NS slots x [32 columns][ROWS]
 	L.red = o; o += (size_t) WG * NJ * 4;                          // per-warp partial phi [WG][NJ]
 	L.xbuf = o; o += C > 1 ? (size_t) 2 * C * (NJ + 4) * 4 : 0;    // incoming partials [parity][C][NJ + 4]
@@ -156,19 +158,14 @@ __host__ __device__ constexpr TmemSmem tmem_smem_layout(int C, int NU, int WG) {
 	return L;
 }
 
-template <int C, int NU, int WG>
+template <int C, int WG>
 __global__ void __launch_bounds__(256, 1)
 k_estep_tmem(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, int64_t doc_offset, int64_t count) {
 	constexpr int G = 8 / WG;                  // groups (documents in flight) per CTA
 	constexpr int GT = 32 * WG;                // threads per group
 	constexpr int ROWS = 64 * WG;              // topic rows per CTA
-	constexpr int NJ = 32 * NU;                // column capacity
-	constexpr int XS = NJ + 4;                 // floats per rank slot of the exchange buffer (the delta sits at [NJ])
-	constexpr int UT = NU < kTmemBlocks ? NU : kTmemBlocks;   // column blocks in TMEM
-	constexpr int UR = NU - UT;                // column blocks in registers
-	constexpr int NCW = (NJ + GT - 1) / GT;    // columns per weight thread
-	constexpr int NS = NU < 3 ? NU : 3;        // landing slots (chunks of 32 columns in flight)
-	constexpr TmemSmem L = tmem_smem_layout(C, NU, WG);
+	constexpr int NS = 3;                      // landing slots (chunks of 32 columns in flight)
+	constexpr TmemSmem L = tmem_smem_layout(C, kTmemMaxBlocks, WG);   // buffers sized for the widest tile shape
 	extern __shared__ __align__(128) unsigned char smem[];
 	__shared__ uint32_t tmem_base_slot;
 
@@ -278,14 +275,25 @@ k_estep_tmem(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, in
 		}
 	}
 
-	for(int item = team; item < count; item += n_teams) {
+	// One document, tile shape NU (32 NU columns): the body is instantiated per shape and picked per document, so that
+	// ONE persistent launch serves all document lengths (no tail per shape).  The landing ring always sees at least NS
+	// chunks per document (empty ones complete at once), which keeps the look-ahead within the next document.
+	int item = team;
+	auto process = [&](auto shape) {
+		constexpr int NU = decltype(shape)::value;
+		constexpr int RC = NU < NS ? NS : NU;      // chunks of this document in the landing ring
+		constexpr int NJ = 32 * NU;                // column capacity
+		constexpr int XS = NJ + 4;                 // floats per rank slot of the exchange buffer (the delta sits at [NJ])
+		constexpr int UT = NU < kTmemBlocks ? NU : kTmemBlocks;   // column blocks in TMEM
+		constexpr int UR = NU - UT;                // column blocks in registers
+		constexpr int NCW = (NJ + GT - 1) / GT;    // columns per weight thread
 		d = d_next; begin = begin_next; n = n_next;
 		const bool more = item + n_teams < count;
 		if(more)
 			doc_of(item + n_teams, d_next, begin_next, n_next);
-		int ids[NU > NS ? NU - NS : 1];    // word ids of this document's chunks NS ..
+		int ids[RC > NS ? RC - NS : 1];    // word ids of this document's chunks NS ..
 		#pragma unroll
-		for(int u = NS; u < NU; ++u)
+		for(int u = NS; u < RC; ++u)
 			ids[u - NS] = 32 * u + lane < n ? docs.word_ids[begin + 32 * u + lane] : 0;
 		if(more) {
 			#pragma unroll
@@ -312,13 +320,13 @@ k_estep_tmem(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, in
 		// value slot c = 4 i + q of column block u: row 16 lr + (i ^ 2 lc), column lc + 8 (q ^ lr) + 32 u
 		uint32_t Dreg[UR > 0 ? UR : 1][64];
 		#pragma unroll
-		for(int u = 0; u < NU; ++u) {
+		for(int u = 0; u < RC; ++u) {
 			const uint32_t slot = cc % NS;
 			t_mbar_wait(full_addr + 8u * slot, (cc / NS) & 1u);
 			++cc;
 			const float* srow = ring + (size_t) slot * 32 * ROWS + 64 * wg + 16 * lr;
 			#pragma unroll
-			for(int h = 0; h < 2; ++h) {
+			for(int h = 0; h < (u < NU ? 2 : 0); ++h) {
 				uint32_t v[32];    // rows i = 8 h .. 8 h + 7
 				#pragma unroll
 				for(int q = 0; q < 4; ++q) {
@@ -339,10 +347,10 @@ k_estep_tmem(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, in
 				}
 			}
 			t_group_barrier<GT>(g);                 // everybody has read the slot: it may take another chunk
-			if(u + NS < NU)
-				issue_chunk(ids[u + NS < NU ? u : 0], chunk_cols(n, u + NS), (int) slot);
+			if(u + NS < RC)
+				issue_chunk(ids[u + NS < RC ? u : 0], chunk_cols(n, u + NS), (int) slot);
 			else if(more)
-				issue_chunk(ids_next[u + NS - NU < NS ? u + NS - NU : 0], chunk_cols(n_next, u + NS - NU), (int) slot);
+				issue_chunk(ids_next[u + NS - RC < NS ? u + NS - RC : 0], chunk_cols(n_next, u + NS - RC), (int) slot);
 		}
 		asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 
@@ -581,6 +589,17 @@ k_estep_tmem(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, in
 			tk[13] += 1;
 			tk[14] += it + 1;
 		}
+	};
+	for(; item < count; item += n_teams) {
+		const int len = n_next;                    // the document about to be processed
+		if(len <= 64)
+			process(std::integral_constant<int, 2>{});
+		else if(len <= 128)
+			process(std::integral_constant<int, 4>{});
+		else if(len <= 160)
+			process(std::integral_constant<int, 5>{});
+		else
+			process(std::integral_constant<int, 6>{});
 	}
 	if(timing && rank == 0 && g == 0) {
 		for(int i = 0; i < 8; ++i)
@@ -606,54 +625,39 @@ namespace {
 
 struct TmemKernel {
 	const void* fn;
-	int C, NU, WG;
+	int C, WG;
 	size_t smem;
 	int max_clusters;     // co-resident clusters (persistent grid), 0 = not yet known
 };
 
-template <int C, int NU, int WG>
+template <int C, int WG>
 TmemKernel* tmem_kernel() {
 	static TmemKernel k = [] {
 		TmemKernel r{};
-		r.fn = reinterpret_cast<const void*>(&k_estep_tmem<C, NU, WG>);
-		r.C = C; r.NU = NU; r.WG = WG;
-		r.smem = tmem_smem_layout(C, NU, WG).group_total * (8 / WG);
+		r.fn = reinterpret_cast<const void*>(&k_estep_tmem<C, WG>);
+		r.C = C; r.WG = WG;
+		r.smem = tmem_smem_layout(C, kTmemMaxBlocks, WG).group_total * (8 / WG);
 		return r;
 	}();
 	return &k;
 }
 
 // cluster size and group width for K topics: ROWS = 64 WG rows per CTA, C CTAs per document
-template <int NU>
-TmemKernel* tmem_pick(int K) {
+TmemKernel* tmem_select(int K) {
 	// TRLDA_TMEM_WG = 4 / 2: narrower groups, more CTAs per document (experiments: two / four documents per SM)
 	static const int forced = [] { const char* e = getenv("TRLDA_TMEM_WG"); return e ? atoi(e) : 0; }();
 	if(forced == 4 && K > 512 && K <= 1024)
-		return tmem_kernel<4, NU, 4>();
-	if(forced == 2 && K > 512 && K <= 1024)
-		return tmem_kernel<8, NU, 2>();
+		return tmem_kernel<4, 4>();
 	if(K <= 128)
-		return tmem_kernel<1, NU, 2>();
+		return tmem_kernel<1, 2>();
 	if(K <= 256)
-		return tmem_kernel<1, NU, 4>();
+		return tmem_kernel<1, 4>();
 	if(K <= 512)
-		return tmem_kernel<1, NU, 8>();
+		return tmem_kernel<1, 8>();
 	if(K <= 1024)
-		return tmem_kernel<2, NU, 8>();
+		return tmem_kernel<2, 8>();
 	if(K <= 2048)
-		return tmem_kernel<4, NU, 8>();
-	return nullptr;
-}
-
-TmemKernel* tmem_select(int K, int n_max) {
-	if(n_max <= 64)
-		return tmem_pick<2>(K);
-	if(n_max <= 128)
-		return tmem_pick<4>(K);
-	if(n_max <= 160)
-		return tmem_pick<5>(K);
-	if(n_max <= 192)
-		return tmem_pick<6>(K);
+		return tmem_kernel<4, 8>();
 	return nullptr;
 }
 
@@ -665,7 +669,7 @@ int tmem_estep_max_len() { return 192; }
 bool tmem_estep_applicable(int K, int elem_size) {
 	if(elem_size != 4 || K % 4 != 0 || K < 1)
 		return false;
-	return tmem_select(K, 192) != nullptr;
+	return tmem_select(K) != nullptr;
 }
 
 // runs documents order[offset .. offset + count), all of at most n_max <= tmem_estep_max_len() pairs
@@ -673,7 +677,7 @@ int launch_estep_tmem(const EStepArgs& args, const DeviceDocs& docs, const int32
                       int64_t count, int n_max, cudaStream_t s) {
 	if(count == 0)
 		return 0;
-	TmemKernel* k = tmem_select(args.K, n_max);
+	TmemKernel* k = n_max <= tmem_estep_max_len() ? tmem_select(args.K) : nullptr;
 	if(!k)
 		return -1;
 	const int C = k->C, G = 8 / k->WG;
@@ -708,8 +712,7 @@ int launch_estep_tmem(const EStepArgs& args, const DeviceDocs& docs, const int32
 				n = std::min(n, atoi(e));
 		k->max_clusters = n;
 		if(getenv("TRLDA_RESIDENT_VERBOSE"))
-			fprintf(stderr, "[trlda] k_estep_tmem<C=%d, NU=%d, WG=%d>: %zu B shared memory, %d co-resident clusters\n",
-			        C, k->NU, k->WG, k->smem, n);
+			fprintf(stderr, "[trlda] k_estep_tmem<C=%d, WG=%d>: %zu B shared memory, %d co-resident clusters\n", C, k->WG, k->smem, n);
 	}
 	const int64_t teams_needed = (count + G - 1) / G;
 	const int clusters = (int) std::min<int64_t>(k->max_clusters, teams_needed);

@@ -1463,6 +1463,7 @@ __global__ void k_special(int which, const double* __restrict__ x, int64_t n, do
 		case 1: r = trigamma(v); break;
 		case 2: r = lgamma(v); break;
 		case 3: r = exp_digamma_shifted_mixed(v, 0.0); break;
+		case 5: r = exp_digamma_lean(v); break;
 		default: r = exp_digamma_shifted(v, 0.0); break;
 	}
 	out[i] = r;

@@ -921,8 +921,7 @@ int run_estep(trlda_model* m, GammaSource src, const double* host_gamma, int max
 	m->stats.estep_calls++;
 	const bool warm = src == GAMMA_KEEP;
 	// Mixed mode: the tensor-memory-resident cluster kernel (estep_tmem.cu).  The documents are sorted by length, longest
-	// first: [0, len_gt[0]) do not fit the on-chip tile and go to the streaming kernel, the rest is cut by tile shape
-	// (192 / 160 / 128 / 64 columns); a cut that would leave fewer than 64 documents joins the wider shape before it.
+	// first: [0, len_gt[0]) do not fit the on-chip tile and go to the streaming kernel; everything else is one launch.
 	if(!m->force_generic && m->docs.B > 0 && m->tmem_mode && tmem_estep_applicable(m->K, m->beta_elem) &&
 	   (m->len_gt[0] == 0 || stream_estep_applicable(m->K, m->docs.n_max, m->beta_elem, m->smem_optin))) {
 		const int64_t B = m->docs.B;
@@ -933,28 +932,11 @@ int run_estep(trlda_model* m, GammaSource src, const double* host_gamma, int max
 			Launch l(m, KK_ESTEP);
 			launch_estep_stream(a, m->docs, m->b_order.as<int32_t>(), 0, cut[0], m->docs.n_max, m->beta_elem, !warm, m->stream);
 		}
-		struct Range { int64_t begin, end; int shape; };
-		Range pending{cut[0], cut[0], 0};
-		auto flush = [&]() {
-			if(pending.end > pending.begin && ok) {
-				Launch l(m, KK_ESTEP);
-				ok = launch_estep_tmem(a, m->docs, m->b_order.as<int32_t>(), pending.begin, pending.end - pending.begin,
-				                       pending.shape, m->stream) == 0;
-			}
-		};
-		for(int i = 1; i < 5; ++i) {
-			if(cut[i] <= cut[i - 1])
-				continue;
-			if(pending.end == pending.begin)
-				pending = {cut[i - 1], cut[i], cap[i]};
-			else if(cut[i] - cut[i - 1] < 64)
-				pending.end = cut[i];                    // merged: the wider shape covers a few shorter documents
-			else {
-				flush();
-				pending = {cut[i - 1], cut[i], cap[i]};
-			}
+		if(B > cut[0]) {
+			// one persistent launch for all tile shapes: the kernel picks the shape per document
+			Launch l(m, KK_ESTEP);
+			ok = launch_estep_tmem(a, m->docs, m->b_order.as<int32_t>(), cut[0], B - cut[0], cap[1], m->stream) == 0;
 		}
-		flush();
 		if(ok) {
 			m->gamma_valid = true;
 			m->stats.estep_docs = m->docs.B;

@@ -150,20 +150,23 @@ __device__ __forceinline__ float exp_digamma_scaled_f32(double lambda, float ek)
 // (MUFU seed + one fp64 Newton step), five series terms (the sixth is 1e-11 at s = 6), and an inline exp: range
 // reduction by the 1.5 * 2^52 trick, degree-9 Taylor polynomial on |r| <= ln2 / 2, exponent patched into the high
 // word.  The constants sit in constant memory so that they reach the DFMAs as c[bank][offset] operands.
-static __constant__ double kLeanPsi[29] = {
-	15.0, 85.0, 225.0, 274.0, 120.0,                                    // 0..4   D(x) = x (x+1) ... (x+5)
-	75.0, 340.0, 675.0, 548.0,                                          // 5..8   D'(x) (leading 6, trailing 120)
-	1.0 / 132, -1.0 / 240, 1.0 / 252, -1.0 / 120, 1.0 / 12,             // 9..13  B_2k / (2k), k = 5..1
-	1.4426950408889634074, 6755399441055744.0,                          // 14, 15 log2(e), 1.5 * 2^52
-	-6.93147180369123816490e-01, -1.90821492927058770002e-10,           // 16, 17 -ln2 (high, low)
-	1.0 / 362880, 1.0 / 40320, 1.0 / 5040, 1.0 / 720, 1.0 / 120, 1.0 / 24, 1.0 / 6, 0.5, 1.0,   // 18..26 1/k!
-	6.0, 64.0};                                                         // 27, 28
+static __constant__ double kLeanPsi[32] = {
+	120.0, 274.0, 225.0, 85.0, 15.0,                                    // 0..4   D(x) / x = 120 + 274 x + 225 x^2 + 85 x^3 + 15 x^4 + x^5
+	548.0, 675.0, 340.0, 75.0, 6.0,                                     // 5..9   D'(x) = 120 + 548 x + ... + 6 x^5
+	1.0 / 12, -1.0 / 120, 1.0 / 252, -1.0 / 240, 1.0 / 132,             // 10..14 B_2k / (2k), k = 1..5
+	1.4426950408889634074, 6755399441055744.0,                          // 15, 16 log2(e), 1.5 * 2^52
+	-6.93147180369123816490e-01, -1.90821492927058770002e-10,           // 17, 18 -ln2 (high, low)
+	1.0 / 6, 0.5, 1.0 / 120, 1.0 / 24, 1.0 / 5040, 1.0 / 720, 1.0 / 362880, 1.0 / 40320,   // 19..26 1/k! in Estrin pairs
+	64.0, 0.0, 0.0, 0.0, 0.0};                                          // 27
+// Polynomials in Estrin form (pairs, then powers of x^2): the dependent chain is ~28 fp64 operations instead of ~45
+// with Horner's rule — the evaluation is latency-bound, the kernels run two warps per scheduler.
 __device__ __forceinline__ double exp_digamma_lean(double x) {
 	const double* kT = kLeanPsi;
-	const bool big = x >= kT[28];
-	double den = fma(fma(fma(fma(fma(x + kT[0], x, kT[1]), x, kT[2]), x, kT[3]), x, kT[4]), x, 0.0);
-	double num = fma(fma(fma(fma(fma(kT[27], x, kT[5]), x, kT[6]), x, kT[7]), x, kT[8]), x, kT[4]);
-	const double s = big ? x : x + kT[27];
+	const bool big = x >= kT[27];
+	const double x2 = x * x, x4 = x2 * x2;
+	double den = x * fma(x4, x + kT[4], fma(x2, fma(kT[3], x, kT[2]), fma(kT[1], x, kT[0])));
+	double num = fma(x4, fma(kT[9], x, kT[8]), fma(x2, fma(kT[7], x, kT[6]), fma(kT[5], x, kT[0])));
+	const double s = big ? x : x + kT[9];
 	den = big ? 1.0 : den;
 	num = big ? 0.0 : num;
 	const double y = s * den;
@@ -173,23 +176,18 @@ __device__ __forceinline__ double exp_digamma_lean(double x) {
 	q = fma(q, fma(-y, q, 1.0), q);
 	const double r = den * q;                                // 1 / s
 	const double t = fma(num, s, 0.5 * den) * q;             // sum_{i<6} 1/(x+i) + 1/(2s)
-	const double z = r * r;
-	double ser = kT[9];
-	ser = fma(ser, z, kT[10]);
-	ser = fma(ser, z, kT[11]);
-	ser = fma(ser, z, kT[12]);
-	ser = fma(ser, z, kT[13]);
+	const double z = r * r, z2 = z * z;
+	const double ser = fma(z2, fma(z2, kT[14], fma(z, kT[13], kT[12])), fma(z, kT[11], kT[10]));
 	const double u = fma(ser, z, t);                         // exp(psi(x)) = s exp(-u), u > 0
-	double nd = fma(u, kT[14], kT[15]);
+	double nd = fma(u, kT[15], kT[16]);
 	const int n = __double2loint(nd);                        // rint(u log2 e)
-	nd -= kT[15];
-	double rr = fma(nd, kT[16], u);
-	rr = fma(nd, kT[17], rr);                                // u - n ln2
-	double p = kT[18];
-	#pragma unroll
-	for(int i = 19; i <= 26; ++i)
-		p = fma(p, -rr, kT[i]);
-	p = fma(p, -rr, 1.0);                                    // exp(-(u - n ln2))
+	nd -= kT[16];
+	double rr = fma(nd, kT[17], u);
+	rr = fma(nd, kT[18], rr);                                // u - n ln2
+	const double m = -rr, m2 = m * m, m4 = m2 * m2, m8 = m4 * m4;
+	const double p01 = 1.0 + m, p23 = fma(m, kT[19], kT[20]), p45 = fma(m, kT[21], kT[22]), p67 = fma(m, kT[23], kT[24]),
+	             p89 = fma(m, kT[25], kT[26]);
+	const double p = fma(m8, p89, fma(m4, fma(m2, p67, p45), fma(m2, p23, p01)));     // exp(-(u - n ln2))
 	const double res = s * p;
 	const int hi = __double2hiint(res) - (n << 20);          // * 2^-n
 	return n > 1000 ? 0.0 : __hiloint2double(hi, __double2loint(res));
