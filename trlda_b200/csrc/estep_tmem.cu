@@ -149,7 +149,7 @@ __host__ __device__ constexpr TmemSmem tmem_smem_layout(int C, int NU, int WG) {
 	L.ring = o; o += (size_t) NS * 32 * ROWS * 4;                  // landing ring: NS slots x [32 columns][ROWS]
 	L.red = o; o += (size_t) WG * NJ * 4;                          // per-warp partial phi [WG][NJ]
 	L.xbuf = o; o += C > 1 ? (size_t) 2 * C * (NJ + 4) * 4 : 0;    // incoming partials [parity][C][NJ + 4]
-	L.wperm = o; o += (size_t) 128 * NU * 4;                       // token weights in lane order [lane][NU][4]
+	L.wperm = o; o += (size_t) 256 * NU * 4;                       // token weights, duplicated, [NU][2][lane][2 x 2]
 	L.dl = o; o += (size_t) WG * 4 + 16;                           // per-warp |delta gamma| sums
 	o = (o + 15) & ~size_t(15);
 	L.bars = o; o += 40;                                           // xbar[2], full[3]
@@ -317,7 +317,8 @@ k_estep_tmem(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, in
 			tk[15] = clock64();
 
 		// ---- tile: landing ring -> TMEM / registers, chunk by chunk --------------------------------------------------
-		// value slot c = 4 i + q of column block u: row 16 lr + (i ^ 2 lc), column lc + 8 (q ^ lr) + 32 u
+		// value slot c = 8 (i / 2) + 2 q + i % 2 of column block u: row 16 lr + (i ^ 2 lc), column lc + 8 (q ^ lr) + 32 u;
+		// rows 2 m, 2 m + 1 of a column sit in adjacent registers: the operand pairs of the packed FFMA2 of both passes
 		uint32_t Dreg[UR > 0 ? UR : 1][64];
 		#pragma unroll
 		for(int u = 0; u < RC; ++u) {
@@ -334,8 +335,8 @@ k_estep_tmem(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, in
 					#pragma unroll
 					for(int i2 = 0; i2 < 4; ++i2) {
 						const float2 pr = *reinterpret_cast<const float2*>(col + ((8 * h + 2 * i2) ^ (2 * lc)));
-						v[4 * (2 * i2) + q] = __float_as_uint(pr.x);
-						v[4 * (2 * i2 + 1) + q] = __float_as_uint(pr.y);
+						v[8 * i2 + 2 * q] = __float_as_uint(pr.x);
+						v[8 * i2 + 2 * q + 1] = __float_as_uint(pr.y);
 					}
 				}
 				if(u < UT)
@@ -363,10 +364,9 @@ k_estep_tmem(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, in
 		}
 		float delta_local = 0.f;
 		float delta_total = 0.f;
-		float W[NU][4];        // token weights of this lane's columns, slot (q, u)
 		TRLDA_TTICK(0)
 
-		// one column block of the tile: 64 values, slot c = 4 i + q
+		// half a column block of the tile: 32 values, rows i = 8 h .. 8 h + 7
 		auto block_half = [&](int u, int h, uint32_t (&r)[32]) {
 			if(u < UT)
 				tmem_ld32(taddr + 64u * u + 32u * h, r);
@@ -379,39 +379,37 @@ k_estep_tmem(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, in
 
 		// pass A + exchange: phi of the current etheta -> token weights of this lane's columns
 		auto pass_a = [&]() {
-			float es[16];
+			u64 es2[8];            // etheta of the row pairs 16 lr + ((2 m, 2 m + 1) ^ 2 lc)
 			#pragma unroll
-			for(int i = 0; i < 16; ++i)
-				es[i] = __shfl_xor_sync(0xffffffffu, ef[i & 1], i >> 1);   // etheta of row 16 lr + (i ^ 2 lc)
-			u64 phi2[NU][2];
+			for(int m = 0; m < 8; ++m)
+				es2[m] = t_pack2(__shfl_xor_sync(0xffffffffu, ef[0], m), __shfl_xor_sync(0xffffffffu, ef[1], m));
+			float phiP[NU];
 			#pragma unroll
 			for(int u = 0; u < NU; ++u) {
+				u64 phi2[4];       // per column q: (even rows, odd rows)
 				#pragma unroll
 				for(int h = 0; h < 2; ++h) {
 					uint32_t r[32];
 					block_half(u, h, r);
 					#pragma unroll
-					for(int ii = 0; ii < 8; ++ii) {
-						const u64 e2 = t_pack2(es[8 * h + ii], es[8 * h + ii]);
+					for(int i2 = 0; i2 < 4; ++i2)
 						#pragma unroll
-						for(int t = 0; t < 2; ++t) {
-							const u64 dd = t_pack2u(r[4 * ii + 2 * t], r[4 * ii + 2 * t + 1]);
-							phi2[u][t] = (h == 0 && ii == 0) ? t_fmul2(dd, e2) : t_ffma2(dd, e2, phi2[u][t]);
+						for(int q = 0; q < 4; ++q) {
+							const u64 dd = t_pack2u(r[8 * i2 + 2 * q], r[8 * i2 + 2 * q + 1]);
+							phi2[q] = (h == 0 && i2 == 0) ? t_fmul2(dd, es2[0]) : t_ffma2(dd, es2[4 * h + i2], phi2[q]);
 						}
-					}
 				}
-			}
-			// butterfly over lr (lane bits 3, 4): slots q = 2, 3 go to lane ^ 16, then slot 1 to lane ^ 8
-			float phiP[NU];
-			u64 s2[NU];
-			#pragma unroll
-			for(int u = 0; u < NU; ++u)
-				s2[u] = t_fadd2(phi2[u][0], t_shfl_xor2(phi2[u][1], 16));
-			#pragma unroll
-			for(int u = 0; u < NU; ++u) {
-				float lo, hi;
-				t_unpack2(s2[u], lo, hi);
-				phiP[u] = lo + __shfl_xor_sync(0xffffffffu, hi, 8);
+				// butterfly over lr (lane bits 3, 4): slots q = 2, 3 go to lane ^ 16, then slot 1 to lane ^ 8
+				float s[4];
+				#pragma unroll
+				for(int q = 0; q < 4; ++q) {
+					float lo, hi;
+					t_unpack2(phi2[q], lo, hi);
+					s[q] = lo + hi;
+				}
+				s[0] += __shfl_xor_sync(0xffffffffu, s[2], 16);
+				s[1] += __shfl_xor_sync(0xffffffffu, s[3], 16);
+				phiP[u] = s[0] + __shfl_xor_sync(0xffffffffu, s[1], 8);
 			}
 			float dsum = delta_local;
 			#pragma unroll
@@ -467,7 +465,8 @@ k_estep_tmem(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, in
 					delta_total += dl[w];
 			}
 			// one thread per column: phi (partials added in rank / warp order: identical bits in every CTA), weight,
-			// and the weight's place in the four lane permutations [lr][lc][u][q] with q = (j / 8 % 4) ^ lr
+			// and the weight's place in the four lane permutations: lane (p, j % 8) finds it, DUPLICATED (the FFMA2 operand
+			// of pass B), at [u][q / 2][lane][q % 2] with q = (j / 8 % 4) ^ p
 			#pragma unroll
 			for(int c = 0; c < NCW; ++c) {
 				const int j = tg + c * GT;
@@ -488,58 +487,47 @@ k_estep_tmem(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, in
 					Wmine[c] = wj;
 					const int jc = j & 7, jq = (j >> 3) & 3, ju = j >> 5;
 					#pragma unroll
-					for(int p = 0; p < 4; ++p)
-						wperm[((p * 8 + jc) * NU + ju) * 4 + (jq ^ p)] = wj;
+					for(int p = 0; p < 4; ++p) {
+						const int q = jq ^ p;
+						*reinterpret_cast<float2*>(wperm + ((ju * 2 + (q >> 1)) * 32 + p * 8 + jc) * 4 + 2 * (q & 1)) = make_float2(wj, wj);
+					}
 				}
 			}
 			t_group_barrier<GT>(g);
-			#pragma unroll
-			for(int u = 0; u < NU; ++u) {
-				const float4 w4 = *reinterpret_cast<const float4*>(wperm + (lane * NU + u) * 4);
-				W[u][0] = w4.x; W[u][1] = w4.y; W[u][2] = w4.z; W[u][3] = w4.w;
-			}
 			++seq;
 			TRLDA_TTICK(6)
 		};
 
 		// pass B: acc of this lane's two topics = sum_j W_j D[k, j]
 		auto pass_b = [&](float (&acc)[2]) {
-			u64 part2[16];
+			u64 part2[8];          // row pairs (2 m, 2 m + 1)
 			#pragma unroll
 			for(int u = 0; u < NU; ++u) {
-				const u64 w2[2] = {t_pack2(W[u][0], W[u][1]), t_pack2(W[u][2], W[u][3])};
+				const float4 wa = *reinterpret_cast<const float4*>(wperm + ((u * 2) * 32 + lane) * 4);
+				const float4 wb = *reinterpret_cast<const float4*>(wperm + ((u * 2 + 1) * 32 + lane) * 4);
+				const u64 wd[4] = {t_pack2(wa.x, wa.y), t_pack2(wa.z, wa.w), t_pack2(wb.x, wb.y), t_pack2(wb.z, wb.w)};
 				#pragma unroll
 				for(int h = 0; h < 2; ++h) {
 					uint32_t r[32];
 					block_half(u, h, r);
 					#pragma unroll
-					for(int ii = 0; ii < 8; ++ii)
+					for(int q = 0; q < 4; ++q)
 						#pragma unroll
-						for(int t = 0; t < 2; ++t) {
-							const u64 dd = t_pack2u(r[4 * ii + 2 * t], r[4 * ii + 2 * t + 1]);
-							part2[8 * h + ii] = (u == 0 && t == 0) ? t_fmul2(dd, w2[t]) : t_ffma2(dd, w2[t], part2[8 * h + ii]);
+						for(int i2 = 0; i2 < 4; ++i2) {
+							const u64 dd = t_pack2u(r[8 * i2 + 2 * q], r[8 * i2 + 2 * q + 1]);
+							part2[4 * h + i2] = (u == 0 && q == 0) ? t_fmul2(dd, wd[0]) : t_ffma2(dd, wd[q], part2[4 * h + i2]);
 						}
 				}
 			}
-			float v[16];
+			// butterfly over lc (lane bits 0-2): row slots 8..15 go to lane ^ 4, then 4..7 to lane ^ 2, then 2, 3 to lane ^ 1
 			#pragma unroll
-			for(int i = 0; i < 16; ++i) {
-				float lo, hi;
-				t_unpack2(part2[i], lo, hi);
-				v[i] = lo + hi;
-			}
-			// butterfly over lc (lane bits 0-2): slots 8..15 go to lane ^ 4, then 4..7 to lane ^ 2, then 2, 3 to lane ^ 1
+			for(int m = 0; m < 4; ++m)
+				part2[m] = t_fadd2(part2[m], t_shfl_xor2(part2[m ^ 4], 4));
 			#pragma unroll
-			for(int i = 0; i < 8; ++i)
-				v[i] += __shfl_xor_sync(0xffffffffu, v[i ^ 8], 4);
-			#pragma unroll
-			for(int i = 0; i < 4; ++i)
-				v[i] += __shfl_xor_sync(0xffffffffu, v[i ^ 4], 2);
-			#pragma unroll
-			for(int i = 0; i < 2; ++i)
-				v[i] += __shfl_xor_sync(0xffffffffu, v[i ^ 2], 1);
-			acc[0] = v[0];
-			acc[1] = v[1];
+			for(int m = 0; m < 2; ++m)
+				part2[m] = t_fadd2(part2[m], t_shfl_xor2(part2[m ^ 2], 2));
+			part2[0] = t_fadd2(part2[0], t_shfl_xor2(part2[1], 1));
+			t_unpack2(part2[0], acc[0], acc[1]);
 			TRLDA_TTICK(1)
 		};
 
