@@ -266,6 +266,16 @@ k_estep_tmem(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, in
 	#pragma unroll
 	for(int u = 0; u < NS; ++u)
 		ids_next[u] = 0;
+	// Schedule.  A team's first two documents are fixed (items team, team + n_teams); every further one is drawn from
+	// the launch's work counter, longest documents first, TWO documents ahead of its use: the team's leader (rank 0)
+	// draws it when a document starts and hands (document, first pair, pairs) to all threads of the team, in every CTA,
+	// with the per-iteration exchange - so that the document after the current one is always known early enough for
+	// its first chunks to be prefetched.
+	bool has_next = team < count;
+	int after_d = -1, after_begin = 0, after_n = 0;       // the document after the next one (-1: none)
+	if((int64_t) team + n_teams < count)
+		doc_of(team + n_teams, after_d, after_begin, after_n);
+	const bool leader = rank == 0 && tg == GT - 1;
 	if(team < count) {
 		doc_of(team, d_next, begin_next, n_next);
 		#pragma unroll
@@ -278,7 +288,6 @@ k_estep_tmem(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, in
 	// One document, tile shape NU (32 NU columns): the body is instantiated per shape and picked per document, so that
 	// ONE persistent launch serves all document lengths (no tail per shape).  The landing ring always sees at least NS
 	// chunks per document (empty ones complete at once), which keeps the look-ahead within the next document.
-	int item = team;
 	auto process = [&](auto shape) {
 		constexpr int NU = decltype(shape)::value;
 		constexpr int RC = NU < NS ? NS : NU;      // chunks of this document in the landing ring
@@ -288,9 +297,14 @@ k_estep_tmem(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, in
 		constexpr int UR = NU - UT;                // column blocks in registers
 		constexpr int NCW = (NJ + GT - 1) / GT;    // columns per weight thread
 		d = d_next; begin = begin_next; n = n_next;
-		const bool more = item + n_teams < count;
-		if(more)
-			doc_of(item + n_teams, d_next, begin_next, n_next);
+		const bool more = after_d >= 0;
+		has_next = more;
+		if(more) {
+			d_next = after_d; begin_next = after_begin; n_next = after_n;
+		}
+		int drawn = 0;             // leader: the item drawn for the document after the next one
+		if(leader)
+			drawn = 2 * n_teams + atomicAdd(a.work, 1);
 		int ids[RC > NS ? RC - NS : 1];    // word ids of this document's chunks NS ..
 		#pragma unroll
 		for(int u = NS; u < RC; ++u)
@@ -354,6 +368,9 @@ k_estep_tmem(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, in
 				issue_chunk(ids_next[u + NS - RC < NS ? u + NS - RC : 0], chunk_cols(n_next, u + NS - RC), (int) slot);
 		}
 		asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+		int lead_d = -1, lead_begin = 0, lead_n = 0;
+		if(leader && drawn < count)
+			doc_of(drawn, lead_d, lead_begin, lead_n);
 
 		double e[2];
 		float ef[2];
@@ -421,6 +438,11 @@ k_estep_tmem(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, in
 				red[wg * NJ + lane + 32 * u] = phiP[u];
 			if(lane == 0)
 				dl[wg] = dsum;
+			if(C == 1 && leader) {
+				dl[WG] = __int_as_float(lead_d);
+				dl[WG + 1] = __int_as_float(lead_begin);
+				dl[WG + 2] = __int_as_float(lead_n);
+			}
 			t_group_barrier<GT>(g);
 			const uint32_t par = seq & 1u;
 			const float* xb = xbuf + (size_t) par * C * XS;
@@ -432,11 +454,13 @@ k_estep_tmem(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, in
 					#pragma unroll
 					for(int w = 1; w < WG; ++w)
 						dt += dl[w];
-					asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "n"(C * (NJ * 4 + 4)) : "memory");
+					asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "n"(C * (NJ * 4 + 16)) : "memory");
+					// {delta, the leader's draw}: the last three words count from rank 0 only
 					#pragma unroll
 					for(int r = 0; r < C; ++r)
-						asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
-							::"r"(t_map_to_rank(slot + NJ * 4u, r)), "r"(__float_as_uint(dt)), "r"(t_map_to_rank(mbar, r)) : "memory");
+						asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+							::"r"(t_map_to_rank(slot + NJ * 4u, r)), "r"(__float_as_uint(dt)), "r"(lead_d), "r"(lead_begin), "r"(lead_n),
+							  "r"(t_map_to_rank(mbar, r)) : "memory");
 				}
 				for(int j4 = tg; j4 < NJ / 4; j4 += GT) {
 					float4 s = *reinterpret_cast<const float4*>(red + 4 * j4);
@@ -458,11 +482,17 @@ k_estep_tmem(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, in
 				#pragma unroll
 				for(int r = 1; r < C; ++r)
 					delta_total += xb[r * XS + NJ];
+				after_d = __float_as_int(xb[NJ + 1]);
+				after_begin = __float_as_int(xb[NJ + 2]);
+				after_n = __float_as_int(xb[NJ + 3]);
 			} else {
 				delta_total = dl[0];
 				#pragma unroll
 				for(int w = 1; w < WG; ++w)
 					delta_total += dl[w];
+				after_d = __float_as_int(dl[WG]);
+				after_begin = __float_as_int(dl[WG + 1]);
+				after_n = __float_as_int(dl[WG + 2]);
 			}
 			// one thread per column: phi (partials added in rank / warp order: identical bits in every CTA), weight,
 			// and the weight's place in the four lane permutations: lane (p, j % 8) finds it, DUPLICATED (the FFMA2 operand
@@ -578,7 +608,7 @@ k_estep_tmem(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, in
 			tk[14] += it + 1;
 		}
 	};
-	for(; item < count; item += n_teams) {
+	while(has_next) {
 		const int len = n_next;                    // the document about to be processed
 		if(len <= 64)
 			process(std::integral_constant<int, 2>{});
@@ -594,6 +624,15 @@ k_estep_tmem(EStepArgs a, DeviceDocs docs, const int32_t* __restrict__ order, in
 			atomicAdd(a.ticks + i, (unsigned long long) tk[i]);
 		atomicAdd(a.ticks + 14, (unsigned long long) tk[14]);
 		atomicAdd(a.ticks + 15, (unsigned long long) tk[13]);
+	}
+	if(timing && rank == 0) {
+		// load balance of the static schedule: busiest team against the mean
+		long long busy = 0;
+		for(int i = 0; i < 8; ++i)
+			busy += tk[i];
+		atomicMax(a.ticks + 8, (unsigned long long) busy);
+		atomicAdd(a.ticks + 9, (unsigned long long) busy);
+		atomicAdd(a.ticks + 10, 1ull);
 	}
 	#undef TRLDA_TTICK
 	if(C > 1) {
@@ -702,6 +741,8 @@ int launch_estep_tmem(const EStepArgs& args, const DeviceDocs& docs, const int32
 		if(getenv("TRLDA_RESIDENT_VERBOSE"))
 			fprintf(stderr, "[trlda] k_estep_tmem<C=%d, WG=%d>: %zu B shared memory, %d co-resident clusters\n", C, k->WG, k->smem, n);
 	}
+	if(!args.work || cudaMemsetAsync(args.work, 0, sizeof(int), s) != cudaSuccess)     // the launch's work counter
+		return -1;
 	const int64_t teams_needed = (count + G - 1) / G;
 	const int clusters = (int) std::min<int64_t>(k->max_clusters, teams_needed);
 	cfg.gridDim = dim3((unsigned) (clusters * C));

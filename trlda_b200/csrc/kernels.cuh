@@ -72,6 +72,7 @@ struct EStepArgs {
 	int max_iter = 0;
 	double threshold = 0;
 	unsigned long long* sweeps = nullptr;  // optional counter: += inner iterations + 1 per document (tile sweeps)
+	int* work = nullptr;                   // k_estep_tmem: work counter of the launch (documents handed out so far)
 	unsigned long long* ticks = nullptr;   // optional phase timers (debug, TRLDA_ESTEP_TICKS=1): 16 sums of clock64 deltas
 };
 

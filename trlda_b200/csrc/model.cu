@@ -918,6 +918,7 @@ int run_estep(trlda_model* m, GammaSource src, const double* host_gamma, int max
 	a.threshold = threshold;
 	a.ticks = m->ticks.as<unsigned long long>();
 	a.sweeps = m->sweeps.as<unsigned long long>();
+	a.work = reinterpret_cast<int*>(m->sweeps.as<unsigned long long>() + 1);
 	m->stats.estep_calls++;
 	const bool warm = src == GAMMA_KEEP;
 	// Mixed mode: the tensor-memory-resident cluster kernel (estep_tmem.cu).  The documents are sorted by length, longest
@@ -1822,8 +1823,8 @@ int trlda_create(int kind, int num_words, int num_topics, int64_t num_documents,
 	int status = TRLDA_OK;
 	auto init = [&]() -> int {
 		CUDA_TRY(m, m->lam[0].ensure(kv_bytes(m)));
-		CUDA_TRY(m, m->sweeps.ensure(sizeof(unsigned long long)));
-		CUDA_TRY(m, cudaMemset(m->sweeps.p, 0, sizeof(unsigned long long)));
+		CUDA_TRY(m, m->sweeps.ensure(2 * sizeof(unsigned long long)));    // [0] sweeps, [1] work counter of k_estep_tmem
+		CUDA_TRY(m, cudaMemset(m->sweeps.p, 0, 2 * sizeof(unsigned long long)));
 		TRY(ensure_small(m));
 		TRY(upload_alpha(m));
 		if(kind == TRLDA_KIND_CUMULATIVE) {
@@ -1862,6 +1863,9 @@ void trlda_destroy(trlda_model* m) {
 			for(int i = 0; i < 8; ++i)
 				fprintf(stderr, "[trlda]   %-30s %10.0f cycles/doc %8.0f cycles/exchange\n", resident_names[i],
 				        t[15] ? (double) t[i] / (double) t[15] : 0.0, t[14] ? (double) t[i] / (double) t[14] : 0.0);
+			if(t[10])
+				fprintf(stderr, "[trlda]   busiest team %.0f cycles, mean %.0f over %llu teams (all launches): imbalance %.3f\n", (double) t[8],
+				        (double) t[9] / (double) t[10], t[10], (double) t[8] * (double) t[10] / (double) t[9]);
 		}
 		const bool streamed = m->stream_mode != 0;
 		fprintf(stderr, "[trlda] %s E-step phase timers: %llu documents, %llu %s\n", streamed ? "streaming" : "fast", t[15], t[14],
