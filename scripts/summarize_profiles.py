@@ -81,10 +81,11 @@ if traffic:
 		current.append(i)
 	summary += ['', '## E-step, call by call (%s_estep_traffic.csv)' % tag, '',
 		'`ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sector_hit_rate.pct,'
-		'l1tex__m_xbar2l1tex_read_bytes.sum -k regex:k_estep -c 130 python bench.py --steps 2 --warmup 1 --no-extras`:',
+		'l1tex__m_xbar2l1tex_read_bytes.sum --clock-control none -k regex:k_estep -c 70 python bench.py --steps 2 --warmup 1 --no-extras`:',
 		'three update_parameters steps of ten trust-region iterations each; one E-step call = one k_estep_stream launch for the',
-		'documents of more than 192 pairs + one k_estep_tmem launch per tile shape (192 / 160 / 128 columns).  The tile is read',
-		'from HBM once per call whatever the number of inner iterations; it then lives in tensor memory.', '',
+		'documents of more than 192 pairs + ONE persistent k_estep_tmem launch for all the others (the tile shape is picked per',
+		'document).  The tile is read from HBM once per call whatever the number of inner iterations; it then lives in tensor',
+		'memory.  (Multi-pass metric collection: the ms column is a replay pass with flushed caches, not a bench time.)', '',
 		'| E-step call | launches | ms | HBM read GB | HBM write GB | L2 -> SM GB |', '|---:|---:|---:|---:|---:|---:|']
 	tot = [0., 0., 0., 0.]
 	for c, ids in enumerate(calls):
