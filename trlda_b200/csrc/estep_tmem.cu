@@ -22,17 +22,23 @@
 // updates those TWO topics (gamma, exp(psi(gamma)), lda.cpp:194-197: two independent fp64 chains per lane); after pass
 // A lane l holds the warp's partial phi of columns l + 32 u.  A lane-dependent XOR permutation of the layout (slot i
 // of a lane holds row 16 lr + (i ^ 2 lc); slot (q, u) column lc + 8 (q ^ lr) + 32 u) makes the butterflies plain
-// shfl.bfly + add without selects; the inner products are packed FFMA2 (fma.rn.f32x2).
+// shfl.bfly + add without selects; the inner products are packed FFMA2 (fma.rn.f32x2) whose 64-bit tile operand is
+// the ROW PAIR (2 m, 2 m + 1) of a column, adjacent in registers and TMEM: pass A multiplies it by (etheta_2m,
+// etheta_2m+1), pass B by the duplicated weight (W_j, W_j) - no register moves to form operands in either pass.
 //
 // Per inner iteration ONE exchange: the group's partial phi (summed over its warps in shared memory) and its share of
 // sum |delta gamma| go to every CTA of the cluster by st.async (DSMEM stores completing on the receiver's mbarrier);
 // all CTAs add the partials in rank order — identical bits, identical convergence decisions (lda.cpp:202) — then one
-// thread per column forms the token weight W_j = c_j / phi_j and leaves it in shared memory in the four lane
-// permutations, from where every lane fetches its 4 NU weights with NU 128-bit loads.
+// thread per column forms the token weight W_j = c_j / phi_j and leaves it, duplicated, in shared memory in the four
+// lane permutations, from where every lane fetches the weights of a column block with two 128-bit loads in pass B.
 //
 // The tile arrives from HBM in chunks of 32 columns through a three-slot landing ring in shared memory (cp.async.bulk per
 // column slab, completing on the slot's mbarrier) and is moved to TMEM by tcgen05.st; the first three chunks of a team's
 // NEXT document are requested while the current one still iterates.
+//
+// ONE persistent launch serves all documents of up to 192 pairs: the body is instantiated per tile shape (NU = 2, 4,
+// 5, 6 column blocks) and picked per document; documents are handed out by a work counter, longest first, two
+// documents ahead of their use (the draw travels with the exchange message, see "Schedule" in the kernel).
 #include "kernels.cuh"
 #include "special.cuh"
 
