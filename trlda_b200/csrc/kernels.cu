@@ -679,8 +679,20 @@ __global__ void __launch_bounds__(NT, (NT == 128 && NCH <= 2 ? 5 : 1)) k_scatter
 	};
 	int buf = 0;
 	const int w_begin = a.v1 < 0 ? 0 : a.v0, w_end = a.v1 < 0 ? a.V : a.v1;       // this launch's words
-	if(w_begin + (int) blockIdx.x < w_end)
-		stage_tokens(0, docs.word_ptr[w_begin + blockIdx.x], docs.word_ptr[w_begin + blockIdx.x + 1]);
+	// Token ranges are looked up TWO words ahead and the (document, weight) pairs of the next word's tokens travel
+	// through registers while the current word is processed: none of the dependent loads word_ptr -> tok_src ->
+	// weight is waited for (the first version staged the next word in one go and stalled on that chain before every
+	// word's token loop: 18 % of the stall samples).
+	int t0 = 0, t1 = 0, n0 = 0, n1 = 0;             // token ranges of the current and the next word
+	if(w_begin + (int) blockIdx.x < w_end) {
+		t0 = docs.word_ptr[w_begin + blockIdx.x];
+		t1 = docs.word_ptr[w_begin + blockIdx.x + 1];
+		stage_tokens(0, t0, t1);
+	}
+	if(w_begin + (int) (blockIdx.x + gridDim.x) < w_end) {
+		n0 = docs.word_ptr[w_begin + blockIdx.x + gridDim.x];
+		n1 = docs.word_ptr[w_begin + blockIdx.x + gridDim.x + 1];
+	}
 	__syncthreads();
 	for(int w = w_begin + blockIdx.x; w < w_end; w += gridDim.x) {
 		const int64_t base = (int64_t) w * K;
@@ -703,13 +715,19 @@ __global__ void __launch_bounds__(NT, (NT == 128 && NCH <= 2 ? 5 : 1)) k_scatter
 		for(int i = 0; i < NCH; ++i)
 			acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.0;
 
-		const int t0 = docs.word_ptr[w], t1 = docs.word_ptr[w + 1];
 		// the (document, weight) pairs of the word's tokens were staged into shared memory while the previous word was
-		// processed (one cooperative round of the dependent loads tok_src -> weight instead of one per token group);
-		// now the next word's are requested
-		const int wn = w + gridDim.x;
-		if(wn < w_end)
-			stage_tokens(buf ^ 1, docs.word_ptr[wn], docs.word_ptr[wn + 1]);
+		// processed; now the next word's (document, source index) are requested, and the range of the word after it
+		const int wn = w + gridDim.x, wnn = wn + gridDim.x;
+		int r_doc = 0, r_src = -1;
+		if(wn < w_end && n0 + (int) threadIdx.x < n1) {
+			r_doc = docs.tok_doc[n0 + threadIdx.x];
+			r_src = docs.tok_src[n0 + threadIdx.x];
+		}
+		int nn0 = 0, nn1 = 0;
+		if(wnn < w_end) {
+			nn0 = docs.word_ptr[wnn];
+			nn1 = docs.word_ptr[wnn + 1];
+		}
 		for(int ts = t0; ts < t1; ts += NT) {
 			if(ts > t0) {                                              // words with more than NT tokens: restage in place
 				__syncthreads();
@@ -750,6 +768,8 @@ __global__ void __launch_bounds__(NT, (NT == 128 && NCH <= 2 ? 5 : 1)) k_scatter
 				}
 			}
 		}
+
+		const float r_w = r_src >= 0 ? (float) a.weight[r_src] : 0.f;     // arrives during the epilogue below
 
 		double psum = 0.0;
 		#pragma unroll
@@ -808,8 +828,14 @@ __global__ void __launch_bounds__(NT, (NT == 128 && NCH <= 2 ? 5 : 1)) k_scatter
 			if(threadIdx.x == 0)
 				a.psi_partials[w] = total;
 		}
+		if(r_src >= 0) {
+			s_doc[buf ^ 1][threadIdx.x] = r_doc;
+			s_w[buf ^ 1][threadIdx.x] = r_w;
+		}
 		__syncthreads();       // the next word's tokens are staged, this word's buffer is free
 		buf ^= 1;
+		t0 = n0; t1 = n1;
+		n0 = nn0; n1 = nn1;
 	}
 }
 
