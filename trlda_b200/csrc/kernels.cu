@@ -668,12 +668,18 @@ __global__ void __launch_bounds__(NT, (NT == 128 && NCH <= 2 ? 5 : 1)) k_scatter
 		for(int q = 0; q < 4; ++q)
 			ek[i][q] = (a.fused && a.write_beta && c < chunks) ? (float) exp(-a.psi_rows[4 * c + q]) : 0.0f;
 	}
-	__shared__ int s_doc[2][NT];
+	__shared__ long long s_row[2][NT];     // byte offset of the token's document row in etheta
 	__shared__ float s_w[2][NT];
+	const long long row_bytes = (long long) K * (long long) sizeof(float);
+	// chunk of out-of-range threads (K / 4 not a multiple of NT): they load the last chunk and drop the result
+	int cc[NCH];
+	#pragma unroll
+	for(int i = 0; i < NCH; ++i)
+		cc[i] = min((int) threadIdx.x + i * NT, chunks - 1);
 	auto stage_tokens = [&](int b, int begin, int end) {
 		const int t = begin + (int) threadIdx.x;
 		if(t < end) {
-			s_doc[b][threadIdx.x] = docs.tok_doc[t];
+			s_row[b][threadIdx.x] = (long long) docs.tok_doc[t] * row_bytes;
 			s_w[b][threadIdx.x] = (float) a.weight[docs.tok_src[t]];
 		}
 	};
@@ -740,15 +746,14 @@ __global__ void __launch_bounds__(NT, (NT == 128 && NCH <= 2 ? 5 : 1)) k_scatter
 				float wf[G];
 				#pragma unroll
 				for(int u = 0; u < G; ++u) {
-					const bool live = g + u < n;                             // no dummy gathers for the tail of a group
-					const int dd = live ? s_doc[buf][g + u] : 0;
-					wf[u] = live ? s_w[buf][g + u] : 0.f;
-					const float4* col = reinterpret_cast<const float4*>(etheta + (int64_t) dd * K);
+					// the tail of a group repeats the word's last token with weight 0: unconditional loads (the repeat
+					// hits in L1), no predicates, no zero-filling of the registers
+					const int tt = min(g + u, n - 1);
+					wf[u] = g + u < n ? s_w[buf][tt] : 0.f;
+					const float4* col = reinterpret_cast<const float4*>(reinterpret_cast<const char*>(etheta) + s_row[buf][tt]);
 					#pragma unroll
-					for(int i = 0; i < NCH; ++i) {
-						const int c = threadIdx.x + i * NT;
-						v[u][i] = (live && c < chunks) ? col[c] : make_float4(0.f, 0.f, 0.f, 0.f);
-					}
+					for(int i = 0; i < NCH; ++i)
+						v[u][i] = col[cc[i]];
 				}
 				// float32 products summed over the <= G tokens of the group, float64 across groups
 				#pragma unroll
@@ -829,7 +834,7 @@ __global__ void __launch_bounds__(NT, (NT == 128 && NCH <= 2 ? 5 : 1)) k_scatter
 				a.psi_partials[w] = total;
 		}
 		if(r_src >= 0) {
-			s_doc[buf ^ 1][threadIdx.x] = r_doc;
+			s_row[buf ^ 1][threadIdx.x] = (long long) r_doc * row_bytes;
 			s_w[buf ^ 1][threadIdx.x] = r_w;
 		}
 		__syncthreads();       // the next word's tokens are staged, this word's buffer is free
