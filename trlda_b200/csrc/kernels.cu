@@ -651,8 +651,9 @@ __global__ void __launch_bounds__(SCATTER_THREADS, (KPT <= 8 ? 7 : 1)) k_scatter
 // Vectorised variant for the mixed-precision path (etheta and beta in float32, K a multiple of 4): every thread
 // owns NCH chunks of 4 consecutive topics, so a token costs NCH 128-bit L2 loads per thread instead of 4 NCH
 // 32-bit ones, and lambda' / lambda / beta move as 128-/256-bit streaming accesses.
-template <int NT, int NCH, int G>
-__global__ void __launch_bounds__(NT, (NT == 128 && NCH <= 2 ? 5 : 1)) k_scatter_vec(ScatterArgs a, DeviceDocs docs) {
+// L tokens' gathers are in flight at a time (L a multiple of G); the arithmetic stays in groups of G whatever L is.
+template <int NT, int NCH, int G, int L = G>
+__global__ void __launch_bounds__(NT, (NT == 128 && NCH <= 2 ? (L > 4 ? 4 : 5) : 1)) k_scatter_vec(ScatterArgs a, DeviceDocs docs) {
 	__shared__ double scratch[32];
 	const int K = a.K;
 	const int chunks = K / 4;
@@ -741,11 +742,11 @@ __global__ void __launch_bounds__(NT, (NT == 128 && NCH <= 2 ? 5 : 1)) k_scatter
 				__syncthreads();
 			}
 			const int n = min(NT, t1 - ts);
-			for(int g = 0; g < n; g += G) {
-				float4 v[G][NCH];
-				float wf[G];
+			for(int g = 0; g < n; g += L) {
+				float4 v[L][NCH];
+				float wf[L];
 				#pragma unroll
-				for(int u = 0; u < G; ++u) {
+				for(int u = 0; u < L; ++u) {
 					// the tail of a group repeats the word's last token with weight 0: unconditional loads (the repeat
 					// hits in L1), no predicates, no zero-filling of the registers
 					const int tt = min(g + u, n - 1);
@@ -757,19 +758,24 @@ __global__ void __launch_bounds__(NT, (NT == 128 && NCH <= 2 ? 5 : 1)) k_scatter
 				}
 				// float32 products summed over the <= G tokens of the group, float64 across groups
 				#pragma unroll
-				for(int i = 0; i < NCH; ++i) {
-					float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
+				for(int sg = 0; sg < L; sg += G) {
+					if(sg > 0 && g + sg >= n)
+						break;
 					#pragma unroll
-					for(int u = 0; u < G; ++u) {
-						g0 = fmaf(wf[u], v[u][i].x, g0);
-						g1 = fmaf(wf[u], v[u][i].y, g1);
-						g2 = fmaf(wf[u], v[u][i].z, g2);
-						g3 = fmaf(wf[u], v[u][i].w, g3);
+					for(int i = 0; i < NCH; ++i) {
+						float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
+						#pragma unroll
+						for(int u = sg; u < sg + G; ++u) {
+							g0 = fmaf(wf[u], v[u][i].x, g0);
+							g1 = fmaf(wf[u], v[u][i].y, g1);
+							g2 = fmaf(wf[u], v[u][i].z, g2);
+							g3 = fmaf(wf[u], v[u][i].w, g3);
+						}
+						acc[i][0] += (double) g0;
+						acc[i][1] += (double) g1;
+						acc[i][2] += (double) g2;
+						acc[i][3] += (double) g3;
 					}
-					acc[i][0] += (double) g0;
-					acc[i][1] += (double) g1;
-					acc[i][2] += (double) g2;
-					acc[i][3] += (double) g3;
 				}
 			}
 		}
