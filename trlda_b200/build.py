@@ -45,7 +45,7 @@ def build_library(force=False, verbose=False):
 	headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cuh', '.h'))]
 	headers.append(os.path.join(ROOT, 'include', 'trlda_b200.h'))
 	sources = [os.path.join(CSRC, 'kernels.cu'), os.path.join(CSRC, 'estep_fast.cu'), os.path.join(CSRC, 'estep_stream.cu'),
-		os.path.join(CSRC, 'estep_tmem.cu'), os.path.join(CSRC, 'sample.cu'), os.path.join(CSRC, 'ingest.cu'),
+		os.path.join(CSRC, 'estep_tmem.cu'), os.path.join(CSRC, 'sample.cu'), os.path.join(CSRC, 'csc.cu'), os.path.join(CSRC, 'ingest.cu'),
 		os.path.join(CSRC, 'model.cu')]
 	objects = []
 	rebuilt = False

@@ -119,6 +119,12 @@ void launch_gibbs(const DeviceDocs& docs, int K, const void* beta, int beta_elem
                   const int64_t* occ_ptr, uint16_t* topics, int num_samples, int burn_in, uint64_t seed, double* theta_out,
                   double* sstats, cudaStream_t s);
 
+// csc.cu: word-sorted token list of the gathered (multi-GPU) minibatch restricted to the words [v0, v1), on the device
+size_t global_csc_scratch_ints(int64_t B, int64_t N, int v0, int v1);
+void launch_doc_lengths(const int64_t* doc_ptr, int64_t B, int64_t pad_B, int32_t* out, cudaStream_t s);
+void launch_global_csc(const int32_t* len, const int32_t* ids, int R, int64_t max_B, int64_t max_N, int v0, int v1, int V,
+                       int32_t* scratch, int32_t* word_ptr, int32_t* tok_doc, int32_t* tok_src, cudaStream_t s);
+
 // LDA::sample on the device (sample.cu): row-wise CDFs of beta_k ~ Dirichlet(lambda_k), then one warp per document;
 // tokens / counts / lengths are B x cap, B x cap, B device arrays
 int sample_capacity(double length);

@@ -227,7 +227,7 @@ struct trlda_model {
 		std::vector<int64_t> shard_B, shard_N, doc_off, tok_off;      // per rank: documents, pairs, and where they start
 		std::vector<int64_t> pad_B, pad_N;                             // segment sizes (padded to the largest shard)
 		int64_t B = 0, N = 0;
-		DevBuf len, ids, word_ptr, tok_doc, tok_src, etheta32, weight;
+		DevBuf len, ids, word_ptr, tok_doc, tok_src, etheta32, weight, scratch;
 		DeviceDocs view;                                               // word_ptr / tok_doc / tok_src of the global batch
 	};
 	GlobalDocs gdocs;
@@ -752,14 +752,17 @@ int build_global_docs(trlda_model* m, const int64_t* s_ptr, int64_t B, int64_t N
 		return fail(m, TRLDA_ERR_ARG, "Too many (word, count) pairs in one minibatch.");
 	CUDA_TRY(m, g.len.ensure(sizeof(int32_t) * std::max<int64_t>(g.B, 1)));
 	CUDA_TRY(m, g.ids.ensure(sizeof(int32_t) * std::max<int64_t>(g.N, 1)));
-	CUDA_TRY(m, m->gstage.ensure(sizeof(int32_t) * (size_t) (std::max<int64_t>(g.B, 1) + 3 * std::max<int64_t>(g.N, 1) + m->V + 2)));
-	int32_t* h_len = m->gstage.as<int32_t>();
-	int32_t* h_ids = h_len + std::max<int64_t>(g.B, 1);
-	for(int64_t d = 0; d < g.pad_B[m->rank]; ++d)
-		h_len[g.doc_off[m->rank] + d] = d < B ? (int32_t) (s_ptr[d + 1] - s_ptr[d]) : 0;
-	if(g.pad_B[m->rank])
-		CUDA_TRY(m, cudaMemcpyAsync(g.len.as<int32_t>() + g.doc_off[m->rank], h_len + g.doc_off[m->rank], sizeof(int32_t) * g.pad_B[m->rank],
-		                            cudaMemcpyHostToDevice, m->stream));
+	// TRLDA_GLOBAL_CSC=host: the first version of this function (ids back to the host, sorted by host threads, lists
+	// uploaded); default: everything on the device (csc.cu), no copy and no synchronisation after the sizes are known
+	static const bool host_sort = [] { const char* e = getenv("TRLDA_GLOBAL_CSC"); return e && !strcmp(e, "host"); }();
+	int32_t* h_len = nullptr;
+	int32_t* h_ids = nullptr;
+	if(host_sort) {
+		CUDA_TRY(m, m->gstage.ensure(sizeof(int32_t) * (size_t) (std::max<int64_t>(g.B, 1) + 3 * std::max<int64_t>(g.N, 1) + m->V + 2)));
+		h_len = m->gstage.as<int32_t>();
+		h_ids = h_len + std::max<int64_t>(g.B, 1);
+	}
+	launch_doc_lengths(m->b_doc_ptr.as<int64_t>(), B, g.pad_B[m->rank], g.len.as<int32_t>() + g.doc_off[m->rank], m->stream);
 	if(g.pad_N[m->rank])
 		CUDA_TRY(m, cudaMemsetAsync(g.ids.as<int32_t>() + g.tok_off[m->rank], 0xff, sizeof(int32_t) * g.pad_N[m->rank], m->stream));   // -1: no word
 	if(N)
@@ -767,6 +770,26 @@ int build_global_docs(trlda_model* m, const int64_t* s_ptr, int64_t B, int64_t N
 		                            cudaMemcpyDeviceToDevice, m->stream));
 	TRY(gather_segments(m, g.len.p, g.doc_off, g.pad_B, sizeof(int32_t), ncclInt32));
 	TRY(gather_segments(m, g.ids.p, g.tok_off, g.pad_N, sizeof(int32_t), ncclInt32));
+	if(!host_sort) {
+		const int v0 = word_begin(m, m->rank), v1 = word_begin(m, m->rank + 1);
+		CUDA_TRY(m, g.word_ptr.ensure(sizeof(int32_t) * ((size_t) m->V + 1)));
+		CUDA_TRY(m, g.tok_doc.ensure(sizeof(int32_t) * std::max<int64_t>(g.N, 1)));
+		CUDA_TRY(m, g.tok_src.ensure(sizeof(int32_t) * std::max<int64_t>(g.N, 1)));
+		CUDA_TRY(m, g.scratch.ensure(sizeof(int32_t) * global_csc_scratch_ints(g.B, g.N, v0, v1)));
+		CUDA_TRY(m, g.etheta32.ensure(sizeof(float) * (size_t) m->K * std::max<int64_t>(g.B, 1)));
+		CUDA_TRY(m, g.weight.ensure(sizeof(double) * std::max<int64_t>(g.N, 1)));
+		launch_global_csc(g.len.as<int32_t>(), g.ids.as<int32_t>(), R, g.pad_B[0], g.pad_N[0], v0, v1, m->V, g.scratch.as<int32_t>(),
+		                  g.word_ptr.as<int32_t>(), g.tok_doc.as<int32_t>(), g.tok_src.as<int32_t>(), m->stream);
+		TRY(check_launch(m, "word-sorted token list of the gathered minibatch"));
+		g.view = DeviceDocs{};
+		g.view.B = g.B;
+		g.view.N = g.N;
+		g.view.word_ptr = g.word_ptr.as<int32_t>();
+		g.view.tok_doc = g.tok_doc.as<int32_t>();
+		g.view.tok_src = g.tok_src.as<int32_t>();
+		g.ready = true;
+		return TRLDA_OK;
+	}
 	if(g.B)
 		CUDA_TRY(m, cudaMemcpyAsync(h_len, g.len.p, sizeof(int32_t) * g.B, cudaMemcpyDeviceToHost, m->stream));
 	if(g.N)
@@ -1938,13 +1961,13 @@ void trlda_destroy(trlda_model* m) {
 	for(DevBuf* b : bufs)
 		b->release();
 	{
-		DevBuf* gb[] = {&m->gdocs.len, &m->gdocs.ids, &m->gdocs.word_ptr, &m->gdocs.tok_doc, &m->gdocs.tok_src, &m->gdocs.etheta32, &m->gdocs.weight};
+		DevBuf* gb[] = {&m->gdocs.len, &m->gdocs.ids, &m->gdocs.word_ptr, &m->gdocs.tok_doc, &m->gdocs.tok_src, &m->gdocs.etheta32, &m->gdocs.weight, &m->gdocs.scratch};
 		for(DevBuf* b : gb)
 			b->release();
 		m->gstage.release();
 	}
 	for(auto& slot : m->slots) {
-		DevBuf* gb[] = {&slot.gdocs.len, &slot.gdocs.ids, &slot.gdocs.word_ptr, &slot.gdocs.tok_doc, &slot.gdocs.tok_src, &slot.gdocs.etheta32, &slot.gdocs.weight};
+		DevBuf* gb[] = {&slot.gdocs.len, &slot.gdocs.ids, &slot.gdocs.word_ptr, &slot.gdocs.tok_doc, &slot.gdocs.tok_src, &slot.gdocs.etheta32, &slot.gdocs.weight, &slot.gdocs.scratch};
 		for(DevBuf* b : gb)
 			b->release();
 		DevBuf* sb[] = {&slot.b_doc_ptr, &slot.b_word_ids, &slot.b_counts, &slot.b_word_ptr, &slot.b_tok_doc, &slot.b_tok_src, &slot.b_order};
