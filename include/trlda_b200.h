@@ -202,6 +202,13 @@ TRLDA_API int trlda_get_row_sums(trlda_model* m, double* row_sums_K);   /* sum_w
  * valid until the next trlda_sample / trlda_destroy on it.  Seeded by trlda_seed. */
 TRLDA_API int trlda_sample(trlda_model* m, int64_t num_documents, double length, int collapse, trlda_docs* out);
 
+/* Test hook for the multi-GPU token list (csrc/csc.cu; no counterpart in the reference, where one process sees the whole
+ * minibatch): builds, on the device, the word-sorted token list of a gathered minibatch - `ranks` segments of `max_docs`
+ * documents (len, 0 for padding) and `max_pairs` token slots (ids, -1 for padding) each - restricted to the words
+ * [v0, v1).  Host arrays in and out: word_ptr has num_words + 1 entries, tok_doc / tok_src ranks * max_pairs. */
+TRLDA_API int trlda_debug_global_csc(trlda_model* m, const int32_t* len, const int32_t* ids, int ranks, int64_t max_docs,
+                           int64_t max_pairs, int v0, int v1, int32_t* word_ptr, int32_t* tok_doc, int32_t* tok_src);
+
 /* Native reader for the text format of python/utils/load_documents.py:6-69 (one document per line,
  * `N id:cnt id:cnt ...`, first field ignored): the file is memory-mapped and parsed by a background thread into CSR
  * minibatches of `batch_size` documents (0: the whole file) in pinned host memory, `prefetch` batches ahead of the

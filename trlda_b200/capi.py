@@ -80,6 +80,8 @@ PROTOTYPES = {
 	'trlda_destroy': (None, [C.c_void_p]),
 	'trlda_last_error': (C.c_char_p, [C.c_void_p]),
 	'trlda_sample': (C.c_int, [C.c_void_p, C.c_int64, C.c_double, C.c_int, _P(Docs)]),
+	'trlda_debug_global_csc': (C.c_int, [C.c_void_p, _P(C.c_int32), _P(C.c_int32), C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int,
+		_P(C.c_int32), _P(C.c_int32), _P(C.c_int32)]),
 	'trlda_seed': (None, [C.c_uint64]),
 	'trlda_kind': (C.c_int, [C.c_void_p]),
 	'trlda_precision': (C.c_int, [C.c_void_p]),
@@ -400,6 +402,19 @@ class Model(object):
 		ids = np.ctypeslib.as_array(view.word_ids, shape=(N,)).copy() if N else np.zeros(0, dtype=np.int32)
 		cts = np.ctypeslib.as_array(view.counts, shape=(N,)).copy() if N else np.zeros(0, dtype=np.int32)
 		return CSR(ptr, ids, cts)
+
+	def debug_global_csc(self, lengths, ids, ranks, v0, v1):
+		"""test hook (csrc/csc.cu): word-sorted token list of a gathered minibatch - lengths is ranks x max_docs, ids
+		ranks x max_pairs with -1 padding - restricted to the words [v0, v1); returns (word_ptr, tok_doc, tok_src)"""
+		lengths = np.ascontiguousarray(lengths, dtype=np.int32).reshape(ranks, -1)
+		ids = np.ascontiguousarray(ids, dtype=np.int32).reshape(ranks, -1)
+		i32 = lambda x: x.ctypes.data_as(_P(C.c_int32))
+		word_ptr = np.empty(self.V + 1, dtype=np.int32)
+		tok_doc = np.empty(max(ids.size, 1), dtype=np.int32)
+		tok_src = np.empty(max(ids.size, 1), dtype=np.int32)
+		self._check(self._lib.trlda_debug_global_csc(self.h, i32(lengths), i32(ids), int(ranks), lengths.shape[1], ids.shape[1],
+			int(v0), int(v1), i32(word_ptr), i32(tok_doc), i32(tok_src)))
+		return word_ptr, tok_doc[:int(word_ptr[-1])], tok_src[:int(word_ptr[-1])]
 
 	def row_sums(self):
 		out = np.empty(self.K)

@@ -2298,6 +2298,47 @@ int trlda_lower_bound(trlda_model* m, const trlda_docs* docs, const double* late
 	return TRLDA_OK;
 }
 
+int trlda_debug_global_csc(trlda_model* m, const int32_t* len, const int32_t* ids, int ranks, int64_t max_docs, int64_t max_pairs,
+                           int v0, int v1, int32_t* word_ptr, int32_t* tok_doc, int32_t* tok_src) {
+	std::lock_guard<std::recursive_mutex> lock__(m->mu);
+	TRY(set_device(m));
+	if(!len || !ids || !word_ptr || !tok_doc || !tok_src || ranks < 1 || max_docs < 0 || max_pairs < 0 || v0 < 0 || v1 < v0 || v1 > m->V ||
+	   (int64_t) ranks * max_pairs > INT32_MAX)
+		return fail(m, TRLDA_ERR_ARG, "debug_global_csc: bad arguments.");
+	const int64_t B = (int64_t) ranks * max_docs, N = (int64_t) ranks * max_pairs;
+	DevBuf d_len, d_ids, d_wptr, d_tdoc, d_tsrc, d_scratch;
+	auto run = [&]() -> int {
+		CUDA_TRY(m, d_len.ensure(sizeof(int32_t) * std::max<int64_t>(B, 1)));
+		CUDA_TRY(m, d_ids.ensure(sizeof(int32_t) * std::max<int64_t>(N, 1)));
+		CUDA_TRY(m, d_wptr.ensure(sizeof(int32_t) * ((size_t) m->V + 1)));
+		CUDA_TRY(m, d_tdoc.ensure(sizeof(int32_t) * std::max<int64_t>(N, 1)));
+		CUDA_TRY(m, d_tsrc.ensure(sizeof(int32_t) * std::max<int64_t>(N, 1)));
+		CUDA_TRY(m, d_scratch.ensure(sizeof(int32_t) * global_csc_scratch_ints(B, N, v0, v1)));
+		if(B)
+			CUDA_TRY(m, cudaMemcpyAsync(d_len.p, len, sizeof(int32_t) * B, cudaMemcpyHostToDevice, m->stream));
+		if(N) {
+			CUDA_TRY(m, cudaMemcpyAsync(d_ids.p, ids, sizeof(int32_t) * N, cudaMemcpyHostToDevice, m->stream));
+			CUDA_TRY(m, cudaMemsetAsync(d_tdoc.p, 0xff, sizeof(int32_t) * N, m->stream));
+			CUDA_TRY(m, cudaMemsetAsync(d_tsrc.p, 0xff, sizeof(int32_t) * N, m->stream));
+		}
+		launch_global_csc(d_len.as<int32_t>(), d_ids.as<int32_t>(), ranks, max_docs, max_pairs, v0, v1, m->V, d_scratch.as<int32_t>(),
+		                  d_wptr.as<int32_t>(), d_tdoc.as<int32_t>(), d_tsrc.as<int32_t>(), m->stream);
+		TRY(check_launch(m, "debug_global_csc"));
+		CUDA_TRY(m, cudaMemcpyAsync(word_ptr, d_wptr.p, sizeof(int32_t) * ((size_t) m->V + 1), cudaMemcpyDeviceToHost, m->stream));
+		if(N) {
+			CUDA_TRY(m, cudaMemcpyAsync(tok_doc, d_tdoc.p, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, m->stream));
+			CUDA_TRY(m, cudaMemcpyAsync(tok_src, d_tsrc.p, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, m->stream));
+		}
+		CUDA_TRY(m, cudaStreamSynchronize(m->stream));
+		return TRLDA_OK;
+	};
+	const int status = run();
+	DevBuf* all[] = {&d_len, &d_ids, &d_wptr, &d_tdoc, &d_tsrc, &d_scratch};
+	for(DevBuf* b : all)
+		b->release();
+	return status;
+}
+
 int trlda_sample(trlda_model* m, int64_t num_documents, double length, int collapse, trlda_docs* out) {
 	std::lock_guard<std::recursive_mutex> lock__(m->mu);
 	TRY(set_device(m));
