@@ -1054,14 +1054,26 @@ template <typename TB>
 __global__ void __launch_bounds__(256) k_init_update(int K, int V, double rho, double eta, double scale_k,
                                                      const double* __restrict__ lambda_prime, double* __restrict__ lambda,
                                                      const double* __restrict__ psi_rows, TB* __restrict__ beta,
-                                                     const double* __restrict__ wordcount) {
+                                                     const double* __restrict__ wordcount, bool use_ek) {
+	// float32 beta: exp(-psi(row sum)) once per topic and CTA (shared memory), then the float32 evaluation the fused
+	// M-step kernel uses for every later beta of the step
+	extern __shared__ float init_ek[];
+	const bool fast = sizeof(TB) == 4 && use_ek;
+	if(fast) {
+		for(int k = threadIdx.x; k < K; k += blockDim.x)
+			init_ek[k] = (float) exp(-psi_rows[k]);
+		__syncthreads();
+	}
 	for(int w = blockIdx.x; w < V; w += gridDim.x) {
 		const double target = rho * (eta + scale_k * wordcount[w]);     // onlinelda.cpp:86
 		for(int k = threadIdx.x; k < K; k += blockDim.x) {
 			const int64_t e = (int64_t) w * K + k;
 			const double lam = (1. - rho) * lambda_prime[e] + target;   // onlinelda.cpp:85
 			lambda[e] = lam;
-			beta[e] = (TB) exp_digamma_for<TB>(lam, psi_rows[k]);
+			if(fast)
+				beta[e] = (TB) exp_digamma_scaled_f32(lam, init_ek[k]);
+			else
+				beta[e] = (TB) exp_digamma_for<TB>(lam, psi_rows[k]);
 		}
 	}
 }
@@ -1073,10 +1085,13 @@ void launch_init_update(const DeviceDocs& docs, int K, int V, double rho, double
 	const int grid = std::min(V, sm_count() * 16);
 	if(beta_elem == 8)
 		k_init_update<double><<<grid, block, 0, s>>>(K, V, rho, eta, scale_k, lambda_prime, lambda, psi_rows,
-		                                              static_cast<double*>(beta), wordcount);
+		                                              static_cast<double*>(beta), wordcount, false);
 	else
-		k_init_update<float><<<grid, block, 0, s>>>(K, V, rho, eta, scale_k, lambda_prime, lambda, psi_rows,
-		                                             static_cast<float*>(beta), wordcount);
+	{
+		const bool use_ek = (size_t) K * sizeof(float) <= 48 * 1024;
+		k_init_update<float><<<grid, block, use_ek ? (size_t) K * sizeof(float) : 0, s>>>(K, V, rho, eta, scale_k, lambda_prime, lambda,
+		                                             psi_rows, static_cast<float*>(beta), wordcount, use_ek);
+	}
 }
 
 // ------------------------------------------------------------------------------------------------------------
