@@ -545,3 +545,38 @@ def test_full_size_cfg3_properties(capi):
 
 	assert rel_err_columns(gammas['mixed'], gammas['fp64']) < TOL_MIXED
 	assert rel_err(lams['mixed'], lams['fp64']) < TOL_MIXED
+
+
+def test_documents_do_not_depend_on_the_schedule(capi):
+	"""A document's gamma depends on nothing but the document: the tensor-memory kernel hands documents to teams by a work
+	counter (the order depends on timing), and a permuted minibatch puts every document on another team, in another
+	tile slot - the per-document results must be bitwise the same."""
+	from trlda_b200.synth import gamma_matrix
+	rng = np.random.default_rng(77)
+	K, V, B = 1000, 6000, 640                      # more than twice the 74 teams: most documents are drawn dynamically
+	lam0, g0 = gamma_matrix(K, V, 78), gamma_matrix(K, B, 79)
+	lengths = rng.integers(1, 200, size=B)          # every tile shape, a few documents for the streaming kernel
+	lengths[:8] = rng.integers(193, 260, size=8)
+	lengths[8:12] = 0
+	docs = [[(int(w), int(1 + rng.integers(5))) for w in rng.permutation(V)[:n]] for n in lengths]
+
+	def run(order):
+		ptr = np.zeros(B + 1, dtype=np.int64)
+		ids, cts = [], []
+		for i, d in enumerate(order):
+			ids += [w for w, _ in docs[d]]
+			cts += [c for _, c in docs[d]]
+			ptr[i + 1] = len(ids)
+		model = capi.Model('online', V, K, 100000, .1, .2, precision='mixed')
+		model.lambdas = lam0
+		gamma, _ = model.update_variables(capi.CSR(ptr, np.array(ids, dtype=np.int32), np.array(cts, dtype=np.int32)),
+			np.asfortranarray(g0[:, order]), max_iter=7)
+		model.close()
+		out = np.empty_like(gamma)
+		out[:, order] = gamma
+		return out
+
+	first = run(np.arange(B))
+	assert np.all(np.isfinite(first))
+	for seed in (1, 2):
+		assert np.array_equal(run(np.random.default_rng(seed).permutation(B)), first)
