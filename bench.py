@@ -243,6 +243,25 @@ def cpu_sample(w, docs, lam0, sizes, workload_name):
 	return B / full, full, spent, kind, text
 
 
+def cpu_one_thread_point(w, docs, lam0, b1, workload_name, all_cores_seconds):
+	"""SURVEY section 8d asks for the CPU arm at one thread beside all cores (the reference serialises its accumulation
+	with `omp critical`): the smallest sample point again with the OpenMP team cut to one thread."""
+	import ctypes
+	try:
+		gomp = ctypes.CDLL('libgomp.so.1')
+		gomp.omp_get_max_threads.restype = ctypes.c_int
+		before = int(gomp.omp_get_max_threads())
+		gomp.omp_set_num_threads(1)
+	except (OSError, AttributeError):
+		return None
+	try:
+		seconds = cpu_timed_call(w, docs, lam0, b1, 1, workload_name)
+	finally:
+		gomp.omp_set_num_threads(before)
+	return {'sample': 'updateParameters(B=%d, max_iter_tr=1)' % b1, 'one_thread_seconds': seconds,
+		'all_cores_seconds': all_cores_seconds, 'cores': before}
+
+
 def reference_arm(args, w):
 	"""One REAL update_parameters step of the reference's CPU implementation at the workload's full size (cfg-3: B=8192,
 	T=10: about a minute), gamma0 injected; the three-point model of cpu_sample() is run afterwards as a cross-check.
@@ -271,7 +290,8 @@ def reference_arm(args, w):
 		'data': 'synthetic', 'extrapolated': False,
 		'config': {'workload': w['desc'], 'global_batch': B, 'parallelism': 'host cores (OpenMP), %d threads' % cores},
 		'cpu_baseline': {'value': value, 'unit': 'docs/s', 'cores': cores, 'kind': kind, 'sample': sample,
-			'extrapolated': False, 'cross_check_model_docs_per_s': model_value},
+			'extrapolated': False, 'cross_check_model_docs_per_s': model_value,
+			'one_thread': cpu_one_thread_point(w, docs, lam0, 64, args.workload, cpu_timed_call(w, docs, lam0, 64, 1, args.workload))},
 		'e2e': {'value': value, 'unit': 'docs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
 		'gpu_launches': 0}
 	print(json.dumps(line), flush=True)
