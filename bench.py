@@ -524,19 +524,26 @@ def e2e_python(run, w, precision, lam0, batches_np, steps):
 	as in the reference's examples (load_documents returns it)"""
 	import trlda
 	from trlda_b200.synth import to_lists
-	model = trlda.models.OnlineLDA(num_words=w['V'], num_topics=w['K'], num_documents=w['D'], alpha=w['alpha'], eta=w['eta'],
-		device=run.local_rank, precision=precision)
-	model.lambdas = lam0
-	lists = [to_lists(*b) for b in batches_np[:steps + 1]]
 	params = dict(w['params'])
-	model.update_parameters(lists[0], **params)
-	t0 = time.perf_counter()
-	for i in range(steps):
-		model.update_parameters(lists[1 + i % (len(lists) - 1)] if len(lists) > 1 else lists[0], **params)
-	_ = model.eta
-	s = (time.perf_counter() - t0) / steps
+
+	def timed(inputs):
+		# the same model state and the same minibatches for both input forms: the difference is the list walk alone
+		model = trlda.models.OnlineLDA(num_words=w['V'], num_topics=w['K'], num_documents=w['D'], alpha=w['alpha'], eta=w['eta'],
+			device=run.local_rank, precision=precision)
+		model.lambdas = lam0
+		model.update_parameters(inputs[0], **params)
+		t0 = time.perf_counter()
+		for i in range(steps):
+			model.update_parameters(inputs[1 + i % (len(inputs) - 1)] if len(inputs) > 1 else inputs[0], **params)
+		_ = model.eta
+		return (time.perf_counter() - t0) / steps, getattr(model, 'precision', precision)
+
+	s, mode = timed([to_lists(*b) for b in batches_np[:steps + 1]])
+	s_csr, _ = timed([tuple(b) for b in batches_np[:steps + 1]])
 	return {'value': w['B'] / s, 'unit': 'docs/s', 'ms_per_step': s * 1e3, 'steps': steps,
-		'api': 'trlda.models.OnlineLDA.update_parameters(list of lists of (word_id, count))', 'precision': getattr(model, 'precision', precision)}
+		'api': 'trlda.models.OnlineLDA.update_parameters(list of lists of (word_id, count))', 'precision': mode,
+		'same_steps_with_csr_input': {'value': w['B'] / s_csr, 'ms_per_step': s_csr * 1e3,
+			'api': 'update_parameters((doc_ptr, word_ids, counts)): the binding\'s numpy CSR form, no list walk'}}
 
 
 def e2e_file(run, w, precision, lam0, batches_np, steps):

@@ -73,3 +73,38 @@ def test_host_samplers():
 		random_select(10, 4)                                          # utils_test.py:29
 	x = sample_dirichlet(10, 7, .5)
 	assert x.shape == (10, 7) and np.allclose(x.sum(0), 1.)
+
+
+def test_list_walk_of_the_binding():
+	"""list[list[(word, count)]] -> CSR, the conversion every method of the binding applies to `docs` (replaces
+	PyList_ToDocuments, ldainterface.cpp:152-190): the threaded fast path for plain tuples of small ints, the general
+	loop for anything else, the same arrays either way."""
+	import numpy as np
+	from trlda_b200 import _trlda
+	rng = np.random.default_rng(3)
+	lengths = rng.integers(0, 120, size=2000)                    # > 65536 pairs: the threaded path; empty documents too
+	docs = [[(int(w), int(c)) for w, c in zip(rng.integers(0, 50000, n), rng.integers(1, 9, n))] for n in lengths]
+	ptr, ids, cts = _trlda._pack_documents(docs)
+	assert ptr.dtype == np.int64 and ids.dtype == np.int32 and cts.dtype == np.int32
+	assert np.array_equal(ptr, np.concatenate([[0], np.cumsum(lengths)]))
+	assert np.array_equal(ids, np.array([w for d in docs for w, _ in d], dtype=np.int32))
+	assert np.array_equal(cts, np.array([c for d in docs for _, c in d], dtype=np.int32))
+
+	mixed = [list(d) for d in docs]
+	mixed[7] = [(np.int64(w), np.int32(c)) for w, c in mixed[7]] or [(np.int64(3), np.int32(1))]    # not exact ints
+	mixed[11] = mixed[11] + [(2 ** 31 - 1, 5)]                  # the largest value that fits
+	got = _trlda._pack_documents(mixed)
+	want = _trlda._pack_documents([[(int(w), int(c)) for w, c in d] for d in mixed])
+	assert all(np.array_equal(a, b) for a, b in zip(got, want))
+
+	small = _trlda._pack_documents(docs[:5])                     # below the threshold: the serial loop
+	assert np.array_equal(small[1], ids[:small[1].size])
+
+	with pytest.raises(OverflowError):
+		_trlda._pack_documents(docs[:3] + [[(2 ** 31, 1)]])
+	with pytest.raises(OverflowError):
+		_trlda._pack_documents(docs + [[(2 ** 40, 1)]])           # a big int in a large batch: general loop, same error
+	with pytest.raises(TypeError):
+		_trlda._pack_documents([(1, 2)])                           # a document that is not a list
+	with pytest.raises(TypeError):
+		_trlda._pack_documents('docs')

@@ -25,6 +25,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "trlda_b200.h"
@@ -90,16 +91,90 @@ int docs_converter(PyObject* obj, void* out_) {
 	}
 	out.word_ids.resize(total);
 	out.counts.resize(total);
+#if PY_VERSION_HEX >= 0x030C0000
+	// Fast path for the common case - exact tuples of two small exact ints: a few threads walk disjoint document ranges.
+	// They only READ object memory (list / tuple item slots, the int's inline digit), no reference counts, no API that
+	// touches interpreter state; the calling thread holds the GIL throughout, so nothing can mutate the lists.  Anything
+	// unusual (another sequence type, an int subclass, a big int, a value beyond int32) makes the whole batch take the
+	// general loop below, which also produces the reference's error messages.
+	if(total >= 65536) {
+		const int T = (int) std::max(1u, std::min(4u, std::thread::hardware_concurrency() / 2));
+		std::vector<char> unusual((size_t) T, 0);
+		auto walk = [&](int th) {
+			const Py_ssize_t d0 = B * th / T, d1 = B * (th + 1) / T;
+			for(Py_ssize_t d = d0; d < d1; ++d) {
+				PyObject* doc = PyList_GET_ITEM(obj, d);
+				const Py_ssize_t n = (Py_ssize_t) (out.doc_ptr[d + 1] - out.doc_ptr[d]);
+				int32_t* ids = out.word_ids.data() + out.doc_ptr[d];
+				int32_t* cts = out.counts.data() + out.doc_ptr[d];
+				for(Py_ssize_t j = 0; j < n; ++j) {
+					PyObject* pair = PyList_GET_ITEM(doc, j);
+					if(!PyTuple_CheckExact(pair) || PyTuple_GET_SIZE(pair) != 2) {
+						unusual[th] = 1;
+						return;
+					}
+					PyObject* a = PyTuple_GET_ITEM(pair, 0);
+					PyObject* b = PyTuple_GET_ITEM(pair, 1);
+					if(!PyLong_CheckExact(a) || !PyLong_CheckExact(b) || !PyUnstable_Long_IsCompact(reinterpret_cast<PyLongObject*>(a)) ||
+					   !PyUnstable_Long_IsCompact(reinterpret_cast<PyLongObject*>(b))) {
+						unusual[th] = 1;
+						return;
+					}
+					const Py_ssize_t w = PyUnstable_Long_CompactValue(reinterpret_cast<PyLongObject*>(a));
+					const Py_ssize_t c = PyUnstable_Long_CompactValue(reinterpret_cast<PyLongObject*>(b));
+					if(w < INT32_MIN || w > INT32_MAX || c < INT32_MIN || c > INT32_MAX) {
+						unusual[th] = 1;
+						return;
+					}
+					ids[j] = (int32_t) w;
+					cts[j] = (int32_t) c;
+				}
+			}
+		};
+		std::vector<std::thread> pool;
+		for(int th = 1; th < T; ++th)
+			pool.emplace_back(walk, th);
+		walk(0);
+		for(auto& th : pool)
+			th.join();
+		bool clean = true;
+		for(char u : unusual)
+			clean = clean && !u;
+		if(clean) {
+			out.view.num_docs = B;
+			out.view.doc_ptr = out.doc_ptr.data();
+			out.view.word_ids = out.word_ids.data();
+			out.view.counts = out.counts.data();
+			return 1;
+		}
+	}
+#endif
+	// The loop chases two pointers per pair (list -> tuple -> int object), every one a likely cache miss at 1.2 M pairs
+	// per minibatch: the tuple eight pairs ahead and the word-id object four pairs ahead are prefetched.
+	auto as_long = [](PyObject* o) -> long {
+#if PY_VERSION_HEX >= 0x030C0000
+		if(PyLong_CheckExact(o) && PyUnstable_Long_IsCompact(reinterpret_cast<PyLongObject*>(o)))
+			return (long) PyUnstable_Long_CompactValue(reinterpret_cast<PyLongObject*>(o));
+#endif
+		return PyLong_AsLong(o);
+	};
 	size_t t = 0;
 	for(Py_ssize_t d = 0; d < B; ++d) {
 		PyObject* doc = PyList_GET_ITEM(obj, d);
 		const Py_ssize_t n = PyList_GET_SIZE(doc);
 		for(Py_ssize_t j = 0; j < n; ++j, ++t) {
+			if(j + 8 < n)
+				__builtin_prefetch(PyList_GET_ITEM(doc, j + 8));
+			if(j + 4 < n) {
+				PyObject* ahead = PyList_GET_ITEM(doc, j + 4);
+				if(PyTuple_Check(ahead) && PyTuple_GET_SIZE(ahead) == 2)
+					__builtin_prefetch(PyTuple_GET_ITEM(ahead, 0));
+			}
 			PyObject* pair = PyList_GET_ITEM(doc, j);
 			long w, c;
 			if(PyTuple_Check(pair) && PyTuple_GET_SIZE(pair) == 2) {
-				w = PyLong_AsLong(PyTuple_GET_ITEM(pair, 0));
-				c = PyLong_AsLong(PyTuple_GET_ITEM(pair, 1));
+				w = as_long(PyTuple_GET_ITEM(pair, 0));
+				c = as_long(PyTuple_GET_ITEM(pair, 1));
 				if((w == -1 || c == -1) && PyErr_Occurred())
 					return 0;
 			} else if(!PyArg_ParseTuple(pair, "ll", &w, &c)) {                                // ldainterface.cpp:178
@@ -851,7 +926,33 @@ void fill_type(PyTypeObject& t, const char* name, const char* doc, PyTypeObject*
 	}
 }
 
+// _pack_documents(docs) -> (doc_ptr, word_ids, counts): the binding's list walk on its own, as numpy CSR arrays - what
+// every method does with its `docs` argument before it calls the C ABI (no device needed; used by tests and to time it)
+PyObject* module_pack_documents(PyObject*, PyObject* args) {
+	Documents documents;
+	if(!PyArg_ParseTuple(args, "O&", &docs_converter, &documents))
+		return nullptr;
+	const npy_intp B1 = (npy_intp) documents.view.num_docs + 1;
+	const npy_intp N = (npy_intp) documents.view.doc_ptr[documents.view.num_docs];
+	PyObject* ptr = PyArray_SimpleNew(1, &B1, NPY_INT64);
+	PyObject* ids = PyArray_SimpleNew(1, &N, NPY_INT32);
+	PyObject* cts = PyArray_SimpleNew(1, &N, NPY_INT32);
+	if(!ptr || !ids || !cts) {
+		Py_XDECREF(ptr); Py_XDECREF(ids); Py_XDECREF(cts);
+		return nullptr;
+	}
+	memcpy(PyArray_DATA((PyArrayObject*) ptr), documents.view.doc_ptr, sizeof(int64_t) * B1);
+	if(N) {
+		memcpy(PyArray_DATA((PyArrayObject*) ids), documents.view.word_ids, sizeof(int32_t) * N);
+		memcpy(PyArray_DATA((PyArrayObject*) cts), documents.view.counts, sizeof(int32_t) * N);
+	}
+	PyObject* result = Py_BuildValue("(OOO)", ptr, ids, cts);
+	Py_DECREF(ptr); Py_DECREF(ids); Py_DECREF(cts);
+	return result;
+}
+
 PyMethodDef module_methods[] = {
+	{"_pack_documents", module_pack_documents, METH_VARARGS, "_pack_documents(docs)\n\nThe binding's list -> CSR conversion on its own."},
 	{"seed", module_seed, METH_VARARGS, "seed(value)\n\nSeeds the generators used for the initial gamma / lambda."},
 	{"polygamma", module_polygamma, METH_VARARGS, "polygamma(n, x)\n\nThe n-th derivative of the digamma function."},
 	{nullptr, nullptr, 0, nullptr}};
