@@ -25,6 +25,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <system_error>
 #include <thread>
 #include <vector>
 
@@ -132,9 +133,16 @@ int docs_converter(PyObject* obj, void* out_) {
 			}
 		};
 		std::vector<std::thread> pool;
-		for(int th = 1; th < T; ++th)
-			pool.emplace_back(walk, th);
+		int started = 1;
+		try {
+			for(int th = 1; th < T; ++th, ++started)
+				pool.emplace_back(walk, th);
+		} catch(const std::system_error&) {
+			// no more threads to be had: the calling thread walks the ranges that got none
+		}
 		walk(0);
+		for(int th = started; th < T; ++th)
+			walk(th);
 		for(auto& th : pool)
 			th.join();
 		bool clean = true;
